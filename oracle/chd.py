@@ -1,0 +1,306 @@
+"""Oracle (test infrastructure): the CHD hot-path driver restated in NumPy.
+
+Follows HELP (helper_functions.py), MAIN (_GraphDiscoveryMain.py), CONT
+(Modes/container.py) and DEC (decision.py) of the reference:
+
+  index matrix / initial masks      CONT:68-96, HELP:20-29, MAIN:423-446
+  activations (3 code paths)        HELP:40-134
+  one prune step                    HELP:166-176
+  stage 1 (kernel performance)      MAIN:448-511
+  kernel choice                     MAIN:513-557, DEC:42-63, 77-100
+  prune loop                        MAIN:559-701
+  anomaly clamp                     MAIN:349-392
+  mode choice                       DEC:150-155, 169-192
+  result extraction                 MAIN:738-817
+"""
+import numpy as np
+
+from . import jaxprng
+from .kernels import make_specs, gram, individual_influence, linear_core
+from .regression import perform_regression_and_find_gamma
+
+
+# --------------------------------------------------------------------------- masks
+def make_index_matrix(names, clusters):
+    """CONT:68-96 (no clusters -> identity, CONT:57-58)."""
+    names = list(names)
+    if clusters is None:
+        clusters = [[nm] for nm in names]
+    idx = {nm: i for i, nm in enumerate(names)}
+    M = np.zeros((len(clusters), len(names)))
+    for c, cl in enumerate(clusters):
+        for nm in cl:
+            M[c, idx[nm]] = 1.0
+    return M
+
+
+def initial_masks(index_matrix, target_indexes, adjacency=None):
+    """HELP:15-29: zero the target's own column (and, with possible_edges,
+    every column j with adj[j, idx] == 0)."""
+    out = []
+    N = index_matrix.shape[1]
+    for idx in target_indexes:
+        non_anc = np.arange(N) == idx
+        if adjacency is not None:
+            non_anc = adjacency[:, idx] == 0
+            non_anc[idx] = True
+        m = index_matrix.copy()
+        m[:, non_anc] = 0.0
+        out.append(m)
+    return np.stack(out, axis=0)
+
+
+# --------------------------------------------------------------------- activations
+def activations(spec, X, yb, ga, active_modes, has_clusters):
+    """make_activation_function HELP:40-134."""
+    energy = -np.dot(ga, yb)
+    empty = np.all(active_modes == 0, axis=1)
+    C = active_modes.shape[0]
+    if spec.name == "linear" and not has_clusters:             # HELP:59-79
+        cols = X[:, np.argmax(active_modes, axis=1)]            # (n, C)
+        vecs = cols * yb[:, None]
+        act = spec.scale * np.sum(vecs, axis=0) ** 2 / energy
+    elif spec.name == "quadratic" and not has_clusters:        # HELP:81-111
+        w = np.sum(active_modes, axis=0)
+        K_all = 2 * (spec.alpha + linear_core(X, X, w))
+        cols = X[:, np.argmax(active_modes, axis=1)]
+        vecs = cols * yb[:, None]                               # (n, C)
+        vsq = cols ** 2 * yb[:, None]
+        quad = np.einsum("ic,ic->c", vecs, K_all @ vecs)
+        act = spec.scale * (quad - np.sum(vsq, axis=0) ** 2) / energy
+    else:                                                       # HELP:113-132
+        w = np.sum(active_modes, axis=0)
+        act = np.empty(C)
+        for c in range(C):
+            if empty[c]:
+                act[c] = 0.0
+                continue
+            M = individual_influence(spec, X, X, w, active_modes[c])
+            act[c] = np.dot(yb, M @ yb)
+        act = act / energy
+    return np.where(empty, 2.0, act)
+
+
+def _argmin_nanfirst(a):
+    nan = np.isnan(a)
+    return int(np.argmax(nan)) if nan.any() else int(np.argmin(a))
+
+
+def prune_step(spec, X, active_modes, ga, yb, key, gamma_min, has_clusters):
+    """make_find_ancestor_function.step HELP:166-176."""
+    act = activations(spec, X, yb, ga, active_modes, has_clusters)
+    j = _argmin_nanfirst(act)
+    active_modes = active_modes.copy()
+    active_modes[j, :] = 0.0
+    K = gram(spec, X, X, np.sum(active_modes, axis=0))
+    yb, noise, zl, zh, gamma, key = perform_regression_and_find_gamma(K, ga, gamma_min, key)
+    return active_modes, yb, gamma, key, act, noise, zl, zh
+
+
+# -------------------------------------------------------------------------- stage 1
+def kernel_performance(specs, X, active_modess, gas, subkeys, gamma_min):
+    """get_kernel_performance MAIN:448-511. Returns dict of arrays (T, nk, ...)
+    plus the stage-1 minimum eigenvalues (T, nk)."""
+    T, nk, n = gas.shape[0], len(specs), X.shape[0]
+    ybs = np.zeros((T, nk, n))
+    noises = np.zeros((T, nk))
+    zlo = np.zeros((T, nk))
+    zhi = np.zeros((T, nk))
+    gammas = np.zeros((T, nk))
+    keys = np.zeros((T, nk, 2), dtype=np.uint32)
+    mineig = np.zeros((T, nk))
+    for k, spec in enumerate(specs):
+        for t in range(T):
+            K = gram(spec, X, X, np.sum(active_modess[t], axis=0))
+            me = np.linalg.eigvalsh(K)[0]
+            mineig[t, k] = me
+            gm = -2 * me if me + gamma_min < 0 else gamma_min           # MAIN:477-479
+            yb, noise, zl, zh, g, key = perform_regression_and_find_gamma(K, gas[t], gm, subkeys[t])
+            if np.isnan(g):                                              # MAIN:493-498
+                noise = 1.0
+            if np.isnan(noise):                                          # MAIN:499-505
+                raise ValueError("The regression has returned NaNs")
+            ybs[t, k], noises[t, k], zlo[t, k], zhi[t, k], gammas[t, k], keys[t, k] = yb, noise, zl, zh, g, key
+    return dict(ybs=ybs, noises=noises, Z_lows=zlo, Z_highs=zhi, gammas=gammas, keys=keys, mineig=mineig)
+
+
+# ------------------------------------------------------------------------- choosers
+def min_noise_kernel_chooser(noises, Z_lows):
+    """MinNoiseKernelChooser DEC:42-63 -> (index or -1, selected_index)."""
+    valid = noises < Z_lows
+    sel = _argmin_nanfirst(np.where(valid, noises, 2.0))
+    return (sel if valid.any() else -1), sel
+
+
+def threshold_kernel_chooser(noises, threshold):
+    """ThresholdKernelChooser DEC:77-100 (an out-of-range gather clamps in JAX)."""
+    valid = noises < threshold
+    nk = noises.shape[0]
+    idx = np.where(valid, np.arange(nk), nk)
+    sel = int(idx.min())
+    ok = sel < nk
+    return (sel if ok else -1), min(sel, nk - 1)
+
+
+def max_increment_mode_chooser(noises):
+    """MaxIncrementModeChooser DEC:150-155."""
+    inc = np.append(noises[1:] - noises[:-1], 1 - noises[-1])
+    nan = np.isnan(inc)
+    return int(np.argmax(nan)) if nan.any() else int(np.argmax(inc))
+
+
+def threshold_mode_chooser(noises, threshold):
+    """ThresholdModeChooser DEC:169-192."""
+    under = noises < threshold
+    if under.any():
+        return int(np.max(np.where(under, np.arange(noises.shape[0]), -1)))
+    return _argmin_nanfirst(noises)
+
+
+def anomaly_clamp(a):
+    """MAIN:349-392 applied to one (T, L+1) array."""
+    anom = np.logical_or(a > 1.05, a < -0.05)
+    first = np.argmax(anom, axis=1)[:, None]
+    anyrow = np.any(anom, axis=1)[:, None]
+    return np.where(np.logical_and(np.arange(a.shape[1])[None, :] >= first, anyrow), 1.0, a)
+
+
+# -------------------------------------------------------------------------- stage 2
+def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, zhi,
+                    loop_number, has_clusters):
+    """prune_ancestors MAIN:559-701 for the targets that chose `spec`."""
+    Tk = gas.shape[0]
+    N = X.shape[1]
+    anc = [np.sum(active_modess, axis=1)]
+    noises, zl, zh, gam, ybl, acts = [noise], [zlo], [zhi], [gammas], [ybs], []
+    active = active_modess.copy()
+    ybs = ybs.copy()
+    keys = keys.copy()
+    gamma_min_kernel = None
+
+    def refresh():
+        out = np.empty(Tk)
+        for t in range(Tk):
+            me = np.linalg.eigvalsh(gram(spec, X, X, np.sum(active[t], axis=0)))[0]
+            out[t] = -2 * me if me + 1e-9 < 0 else 1e-9                 # MAIN:628-631
+        return out
+
+    def one_step():
+        nonlocal active, ybs, keys
+        a_new = np.empty_like(active)
+        yb_new = np.empty_like(ybs)
+        g_new = np.empty(Tk)
+        k_new = np.empty_like(keys)
+        act = np.empty((Tk, active.shape[1]))
+        nz = np.empty(Tk)
+        l = np.empty(Tk)
+        h = np.empty(Tk)
+        for t in range(Tk):
+            (a_new[t], yb_new[t], g_new[t], k_new[t], act[t], nz[t], l[t], h[t]) = prune_step(
+                spec, X, active[t], gas[t], ybs[t], keys[t], gamma_min_kernel[t], has_clusters)
+        active, ybs, keys = a_new, yb_new, k_new
+        return g_new, act, nz, l, h
+
+    for step in range(loop_number):
+        p = N - step - 1
+        if step % 50 == 0 or (p * (p + 1)) / 2 == N:                    # MAIN:622-623
+            gamma_min_kernel = refresh()
+        g_new, act, nz, l, h = one_step()
+        anc.append(np.sum(active, axis=1))
+        noises.append(nz); zl.append(l); zh.append(h); acts.append(act); gam.append(g_new); ybl.append(ybs)
+        if np.all(active == 0):                                         # MAIN:659-660
+            break
+    if loop_number == 0:                                                # MAIN:662-691
+        gamma_min_kernel = refresh()
+        _g, act, _nz, _l, _h = one_step()
+        acts.append(act)
+    return dict(active=np.stack(anc, axis=1), noises=np.stack(noises, axis=1),
+                Z_lows=np.stack(zl, axis=1), Z_highs=np.stack(zh, axis=1),
+                activations=np.stack(acts, axis=1), gammas=np.stack(gam, axis=1),
+                ybs=np.stack(ybl, axis=1))
+
+
+# ------------------------------------------------------------------------------ fit
+def normalize(X):
+    """MAIN:92-105."""
+    std = X.std(axis=0, keepdims=True)
+    if np.any(std == 0):
+        raise ValueError("Some features have a standard deviation of 0.")
+    mean = X.mean(axis=0, keepdims=True)
+    return (X - mean) / std, mean, std
+
+
+def fit(X, names, kernels=None, normalize_data=True, clusters=None, adjacency=None,
+        targets=None, key=None, gamma_min=1e-9, kernel_chooser=("min_noise",),
+        mode_chooser=("max_increment",)):
+    """GraphDiscovery(...).fit(...) restated: MAIN:57-134, 272-421, 703-817.
+
+    kernels: list of (name, scale, l); adjacency: dense N x N with adj[i, j] = 1
+    iff edge i -> j is allowed (MAIN:111-117).  Returns
+      {"stage1": {...}, "chosen_kernel": (T,), "nodes": {name: {...}}, "chains": {k: {...}}}.
+    """
+    names = list(names)
+    X = np.asarray(X, dtype=np.float64)
+    if normalize_data:
+        X, _m, _s = normalize(X)
+    if kernels is None:
+        kernels = [("linear", 2.0, None), ("quadratic", 1.0, None), ("gaussian", 1.0, 1.0)]
+    specs = make_specs(kernels)
+    has_clusters = clusters is not None
+    index_matrix = make_index_matrix(names, clusters)
+    C = index_matrix.shape[0]
+    if targets is None:
+        targets = names
+    tidx = np.array([names.index(t) for t in targets])
+    gas = X[:, tidx].T.copy()
+    active0 = initial_masks(index_matrix, tidx, adjacency)
+    if key is None:
+        key = jaxprng.PRNGKey(0)
+    subkeys = jaxprng.split(key, len(targets) + 1)[1:]                  # MAIN:311-313
+
+    perf = kernel_performance(specs, X, active0, gas, subkeys, gamma_min)
+    T = len(targets)
+    chosen = np.empty(T, dtype=int)
+    sel = np.empty(T, dtype=int)
+    for t in range(T):
+        if kernel_chooser[0] == "min_noise":
+            chosen[t], sel[t] = min_noise_kernel_chooser(perf["noises"][t], perf["Z_lows"][t])
+        else:
+            chosen[t], sel[t] = threshold_kernel_chooser(perf["noises"][t], kernel_chooser[1])
+    ar = np.arange(T)
+    ybs, gammas, skeys = perf["ybs"][ar, sel], perf["gammas"][ar, sel], perf["keys"][ar, sel]
+    noises, zlo, zhi = perf["noises"][ar, sel], perf["Z_lows"][ar, sel], perf["Z_highs"][ar, sel]
+
+    nodes = {}
+    chains = {}
+    for k, spec in enumerate(specs):
+        mask = chosen == k
+        if not mask.any():
+            continue
+        ch = prune_ancestors(spec, X, active0[mask], gas[mask], ybs[mask], gammas[mask], skeys[mask],
+                             noises[mask], zlo[mask], zhi[mask], C - 2, has_clusters)
+        ch["noises"] = anomaly_clamp(ch["noises"])
+        ch["Z_lows"] = anomaly_clamp(ch["Z_lows"])
+        ch["Z_highs"] = anomaly_clamp(ch["Z_highs"])
+        ch["targets"] = [targets[i] for i in np.nonzero(mask)[0]]
+        chosen_modes = []
+        for i, name in enumerate(ch["targets"]):
+            if mode_chooser[0] == "max_increment":
+                cm = max_increment_mode_chooser(ch["noises"][i])
+            else:
+                cm = threshold_mode_chooser(ch["noises"][i], mode_chooser[1])
+            chosen_modes.append(cm)
+            acts = ch["activations"][i]
+            act_c = acts[min(cm, acts.shape[0] - 1)]                    # JAX OOB clamp MAIN:790
+            per_var = np.sum(index_matrix * act_c[:, None], axis=0)     # MAIN:789-791
+            active_vars = ch["active"][i, cm]
+            nodes[name] = dict(
+                kernel_index=k, type=spec.name, active_modes=active_vars.copy(),
+                gamma=float(ch["gammas"][i, cm]), noise=float(ch["noises"][i, cm]),
+                coeff=ch["ybs"][i, cm].copy(), chosen_mode=cm,
+                ancestors=[names[j] for j in range(len(names)) if active_vars[j] == 1],
+                signals={names[j]: float(per_var[j]) for j in range(len(names)) if active_vars[j] == 1})
+        ch["chosen_modes"] = np.array(chosen_modes)
+        chains[k] = ch
+    return dict(stage1=perf, chosen_kernel=chosen, targets=list(targets), nodes=nodes, chains=chains,
+                X=X, specs=specs, index_matrix=index_matrix)
