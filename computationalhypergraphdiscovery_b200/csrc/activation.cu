@@ -1,0 +1,414 @@
+// Per-cluster activations  act_c = yb^T Infl_c yb / energy  for every candidate ancestor cluster of
+// every target in one pass, + argmin + row removal.  Replaces make_activation_function and the
+// first two lines of `step` (helper_functions.py:40-134, 166-169) of the reference.
+//
+// All three kernels reduce to a few contractions, with
+//   g_d   = x_d . yb,   Gm[d][d'] = sum_i x_id yb_i x_id'   (active variables only),
+//   lin_c  = sum_{d in c} g_d^2
+//   quad_c = 2 alpha lin_c + sum_{d in c} sum_{d' active} Gm[d][d']^2 * (d' in c ? 1 : 2)
+//   gau_c  = sum_ij yb_i yb_j P_ij (1 - 1/prod_{d in c}(1 + E_d,ij)),  P = prod_{d active}(1 + E_d)
+//   linear:    s lin_c / energy            (helper_functions.py:69-77 == kernels.py:104-106)
+//   quadratic: s quad_c / energy           (helper_functions.py:92-109 == kernels.py:175-185)
+//   gaussian:  (qs quad_c + s gau_c)/energy (kernels.py:270-278)
+// which equal the reference's expressions term by term (the Hadamard-product quadratic forms
+// yb^T (L_a o L_b) yb are sums of squares of Gm entries).
+#include "internal.cuh"
+
+namespace chd {
+
+// w[t][d] = w0[t][d] && alive[t][cluster_of[d]]
+__global__ void active_vars_kernel(const uint8_t* __restrict__ w0, const uint8_t* __restrict__ alive,
+                                   const int32_t* __restrict__ cluster_of, int N, int C, uint8_t* __restrict__ w) {
+  const int t = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < N) w[(size_t)t * N + d] = (w0[(size_t)t * N + d] && alive[(size_t)t * C + cluster_of[d]]) ? 1 : 0;
+}
+
+int active_vars_launch(const uint8_t* w0, const uint8_t* alive, const int32_t* cluster_of, int N, int C, int T,
+                       uint8_t* w, cudaStream_t st) {
+  active_vars_kernel<<<dim3((N + 127) / 128, T), 128, 0, st>>>(w0, alive, cluster_of, N, C, w);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+// gdot[t][d] = sum_i X[i][d] yb[t][i];  energy[t] = -sum_i ga[t][i] yb[t][i]
+__global__ void __launch_bounds__(256) gdot_kernel(const double* __restrict__ X, int n, int N,
+                                                   const double* __restrict__ yb, const double* __restrict__ ga,
+                                                   double* __restrict__ gdot, double* __restrict__ energy) {
+  __shared__ double red[8][33];
+  const int t = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
+  const double* y = yb + (size_t)t * n;
+  double s = 0.0;
+  if (d < N)
+    for (int i = wid; i < n; i += 8) s += X[(size_t)i * N + d] * y[i];
+  red[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && d < N) {
+    double r = 0.0;
+    for (int q = 0; q < 8; ++q) r += red[q][lane];
+    gdot[(size_t)t * N + d] = r;
+  }
+  if (blockIdx.x == 0) {
+    __shared__ double sred[40];
+    double e = 0.0;
+    const double* g = ga + (size_t)t * n;
+    for (int i = threadIdx.x; i < n; i += 256) e += g[i] * y[i];
+    e = block_sum(e, sred);
+    if (threadIdx.x == 0) energy[t] = -e;
+  }
+}
+
+// Gm[t][d][d'] = sum_i X[i][d] yb_i X[i][d'], 32 x 32 tile per block (all variables; masked later).
+__global__ void __launch_bounds__(256) gmat_kernel(const double* __restrict__ X, int n, int N,
+                                                   const double* __restrict__ yb, double* __restrict__ Gm) {
+  __shared__ double sa[32][33], sb[32][33];
+  const int t = blockIdx.z;
+  const int d0 = blockIdx.y * 32, e0 = blockIdx.x * 32;
+  if (e0 > d0) return;  // symmetric: lower tiles only, mirrored on write
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7
+  const double* y = yb + (size_t)t * n;
+  double acc[4] = {0, 0, 0, 0};
+  for (int i0 = 0; i0 < n; i0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + ty * 4 + r;
+      double xa = 0.0, xb = 0.0;
+      if (i < n) {
+        const double yi = y[i];
+        if (d0 + tx < N) xa = X[(size_t)i * N + d0 + tx] * yi;
+        if (e0 + tx < N) xb = X[(size_t)i * N + e0 + tx];
+      }
+      sa[ty * 4 + r][tx] = xa;
+      sb[ty * 4 + r][tx] = xb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const double b = sb[i][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += sa[i][ty * 4 + r] * b;
+    }
+    __syncthreads();
+  }
+  double* G = Gm + (size_t)t * N * N;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int d = d0 + ty * 4 + r, e = e0 + tx;
+    if (d < N && e < N) {
+      G[(size_t)d * N + e] = acc[r];
+      G[(size_t)e * N + d] = acc[r];
+    }
+  }
+}
+
+// rowq[t][d] = sum_{d' active} Gm[d][d']^2 * (same cluster ? 1 : 2)    (one warp per variable d)
+__global__ void __launch_bounds__(256) quad_rows_kernel(const double* __restrict__ Gm, int N,
+                                                        const uint8_t* __restrict__ w,
+                                                        const int32_t* __restrict__ cluster_of,
+                                                        double* __restrict__ rowq) {
+  const int t = blockIdx.y, lane = threadIdx.x & 31;
+  const int d = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (d >= N) return;
+  const uint8_t* wt = w + (size_t)t * N;
+  double s = 0.0;
+  if (wt[d]) {
+    const int cd = cluster_of[d];
+    const double* row = Gm + ((size_t)t * N + d) * N;
+    for (int e = lane; e < N; e += 32)
+      if (wt[e]) {
+        const double v = row[e];
+        s += v * v * ((cluster_of[e] == cd) ? 1.0 : 2.0);
+      }
+  }
+  s = warp_sum(s);
+  if (lane == 0) rowq[(size_t)t * N + d] = s;
+}
+
+// Gaussian pair sums: partial[t][blk][c] = sum over the block's (i, j) tiles of
+//   sym * yb_i yb_j P_ij (1 - 1/F_c,ij).  XT is N x n (variables major).  Members of cluster c are
+// mem_idx[mem_off[c] .. mem_off[c+1]).
+constexpr int GA_TILE = 64;
+__global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restrict__ XT, int n, int N, int C,
+                                                          const double* __restrict__ yb,
+                                                          const uint8_t* __restrict__ w,
+                                                          const int32_t* __restrict__ mem_off,
+                                                          const int32_t* __restrict__ mem_idx, double inv2l2,
+                                                          double* __restrict__ partial, int nblk) {
+  extern __shared__ double sacc[];  // C x 8 warps
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;
+  const uint8_t* wt = w + (size_t)t * N;
+  const double* y = yb + (size_t)t * n;
+  for (int q = tid; q < C * 8; q += 256) sacc[q] = 0.0;
+  __syncthreads();
+  const int tb = (n + GA_TILE - 1) / GA_TILE;
+  const int ntiles = tb * (tb + 1) / 2;
+  for (int tile = blockIdx.x; tile < ntiles; tile += nblk) {
+    int bi = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= tile) ++bi;
+    while (bi * (bi + 1) / 2 > tile) --bi;
+    const int bj = tile - bi * (bi + 1) / 2;
+    const int i0 = bi * GA_TILE + ty * 4, j0 = bj * GA_TILE + tx * 4;
+    const double sym = (bi == bj) ? 1.0 : 2.0;
+    double P[4][4], yy[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        P[a][b] = 1.0;
+        const int i = i0 + a, j = j0 + b;
+        yy[a][b] = (i < n && j < n) ? sym * y[i] * y[j] : 0.0;
+      }
+    for (int d = 0; d < N; ++d) {
+      if (!wt[d]) continue;
+      const double* xr = XT + (size_t)d * n;
+      double xi[4], xj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        xi[a] = (i0 + a < n) ? __ldg(xr + i0 + a) : 0.0;
+        xj[a] = (j0 + a < n) ? __ldg(xr + j0 + a) : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double df = xi[a] - xj[b];
+          P[a][b] *= 1.0 + exp(-(df * df) * inv2l2);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) P[a][b] *= yy[a][b];
+    for (int c = 0; c < C; ++c) {
+      double F[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) F[a][b] = 1.0;
+      bool any = false;
+      for (int q = mem_off[c]; q < mem_off[c + 1]; ++q) {
+        const int d = mem_idx[q];
+        if (!wt[d]) continue;
+        any = true;
+        const double* xr = XT + (size_t)d * n;
+        double xi[4], xj[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          xi[a] = (i0 + a < n) ? __ldg(xr + i0 + a) : 0.0;
+          xj[a] = (j0 + a < n) ? __ldg(xr + j0 + a) : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const double df = xi[a] - xj[b];
+            F[a][b] *= 1.0 + exp(-(df * df) * inv2l2);
+          }
+      }
+      if (!any) continue;
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s += P[a][b] * (1.0 - 1.0 / F[a][b]);
+      s = warp_sum(s);
+      if (lane == 0) sacc[c * 8 + wid] += s;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += sacc[c * 8 + q];
+    partial[((size_t)t * nblk + blockIdx.x) * C + c] = s;
+  }
+}
+
+// act, argmin and row removal; one block per target.
+__global__ void __launch_bounds__(256) act_finalize_kernel(chd_kernel_desc kd, int N, int C,
+                                                           const uint8_t* __restrict__ w,
+                                                           const int32_t* __restrict__ mem_off,
+                                                           const int32_t* __restrict__ mem_idx,
+                                                           const double* __restrict__ gdot,
+                                                           const double* __restrict__ rowq,
+                                                           const double* __restrict__ gpart, int nblk,
+                                                           const double* __restrict__ energy,
+                                                           uint8_t* __restrict__ alive, double* __restrict__ act,
+                                                           size_t act_stride, int prune, int32_t* __restrict__ pruned,
+                                                           size_t pruned_stride) {
+  __shared__ double s_val[256];
+  __shared__ int s_idx[256];
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const uint8_t* wt = w + (size_t)t * N;
+  const double en = energy[t];
+  double bv = 0.0; int bi = -1; bool bnan = false;
+  for (int c = tid; c < C; c += 256) {
+    double lin = 0.0, qr = 0.0;
+    bool any = false;
+    for (int q = mem_off[c]; q < mem_off[c + 1]; ++q) {
+      const int d = mem_idx[q];
+      if (!wt[d]) continue;
+      any = true;
+      const double g = gdot[(size_t)t * N + d];
+      lin += g * g;
+      if (rowq) qr += rowq[(size_t)t * N + d];
+    }
+    double v;
+    if (!any) {
+      v = 2.0;
+    } else if (kd.kind == CHD_KERNEL_LINEAR) {
+      v = kd.scale * lin / en;
+    } else if (kd.kind == CHD_KERNEL_QUADRATIC) {
+      v = kd.scale * (2.0 * kd.alpha * lin + qr) / en;
+    } else {
+      double gs = 0.0;
+      for (int b = 0; b < nblk; ++b) gs += gpart[((size_t)t * nblk + b) * C + c];
+      v = (kd.quad_scale * (2.0 * kd.alpha * lin + qr) + kd.scale * gs) / en;
+    }
+    act[(size_t)t * act_stride + c] = v;
+    const bool vn = isnan(v);
+    if (bi < 0) { bv = v; bi = c; bnan = vn; }
+    else if (!bnan && (vn || v < bv)) { bv = v; bi = c; bnan = vn; }
+  }
+  if (!prune) return;
+  s_val[tid] = bv; s_idx[tid] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      const double v1 = s_val[tid], v2 = s_val[tid + o];
+      const int i1 = s_idx[tid], i2 = s_idx[tid + o];
+      bool take2;
+      if (i2 < 0) take2 = false;
+      else if (i1 < 0) take2 = true;
+      else {
+        const bool n1 = isnan(v1), n2 = isnan(v2);
+        if (n1 || n2) take2 = n2 && (!n1 || i2 < i1);
+        else take2 = (v2 < v1) || (v2 == v1 && i2 < i1);
+      }
+      if (take2) { s_val[tid] = v2; s_idx[tid] = i2; }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int j = s_idx[0];
+    pruned[(size_t)t * pruned_stride] = j;
+    alive[(size_t)t * C + j] = 0;
+  }
+}
+
+__global__ void transpose_kernel(const double* __restrict__ X, int n, int N, double* __restrict__ XT) {
+  __shared__ double tile[32][33];
+  const int i0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, d = d0 + tx;
+    tile[r][tx] = (i < n && d < N) ? X[(size_t)i * N + d] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int d = d0 + r, i = i0 + tx;
+    if (d < N && i < n) XT[(size_t)d * n + i] = tile[tx][r];
+  }
+}
+
+// cluster membership in CSR form from cluster_of (one thread; N is small)
+__global__ void members_kernel(const int32_t* __restrict__ cluster_of, int N, int C, int32_t* __restrict__ mem_off,
+                               int32_t* __restrict__ mem_idx) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int c = 0; c <= C; ++c) mem_off[c] = 0;
+  for (int d = 0; d < N; ++d) mem_off[cluster_of[d] + 1] += 1;
+  for (int c = 0; c < C; ++c) mem_off[c + 1] += mem_off[c];
+  // stable fill
+  for (int c = 0; c < C; ++c) {
+    int pos = mem_off[c];
+    for (int d = 0; d < N; ++d)
+      if (cluster_of[d] == c) mem_idx[pos++] = d;
+  }
+}
+
+constexpr int GA_BLOCKS = 296;  // 2 per SM
+
+size_t act_workspace(const Plan* pl, int T) {
+  const size_t n = pl->n, N = pl->N, C = pl->C;
+  size_t b = 0;
+  b += align_up(T * N, 256);                                   // w
+  b += align_up((C + 1) * sizeof(int32_t), 256) + align_up(N * sizeof(int32_t), 256);
+  b += 2 * align_up(T * N * sizeof(double), 256);              // gdot, rowq
+  b += align_up(T * sizeof(double), 256);                      // energy
+  b += align_up(T * N * N * sizeof(double), 256);              // Gm
+  b += align_up(n * N * sizeof(double), 256);                  // XT
+  b += align_up((size_t)T * GA_BLOCKS * C * sizeof(double), 256);
+  return b + 4096;
+}
+
+int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const int32_t* cluster_of,
+               const uint8_t* w0, uint8_t* alive, const double* yb, const double* ga, int T, double* act,
+               size_t act_stride, int prune, int32_t* pruned, size_t pruned_stride, void* ws, size_t ws_bytes,
+               cudaStream_t st) {
+  const int n = pl->n, N = pl->N, C = pl->C;
+  Carver cv(ws, ws_bytes);
+  uint8_t* w = cv.take<uint8_t>((size_t)T * N);
+  int32_t* mem_off = cv.take<int32_t>(C + 1);
+  int32_t* mem_idx = cv.take<int32_t>(N);
+  double* gdot = cv.take<double>((size_t)T * N);
+  double* rowq = cv.take<double>((size_t)T * N);
+  double* energy = cv.take<double>(T);
+  double* Gm = cv.take<double>((size_t)T * N * N);
+  double* XT = cv.take<double>((size_t)n * N);
+  double* gpart = cv.take<double>((size_t)T * GA_BLOCKS * C);
+  if (!cv.ok) {
+    set_error("chd_activations: workspace too small (%zu needed, %zu given)", cv.off, ws_bytes);
+    return CHD_ENOSPC;
+  }
+  members_kernel<<<1, 32, 0, st>>>(cluster_of, N, C, mem_off, mem_idx);
+  CHD_LAUNCHED();
+  active_vars_kernel<<<dim3((N + 127) / 128, T), 128, 0, st>>>(w0, alive, cluster_of, N, C, w);
+  CHD_LAUNCHED();
+  gdot_kernel<<<dim3((N + 31) / 32, T), 256, 0, st>>>(X, n, N, yb, ga, gdot, energy);
+  CHD_LAUNCHED();
+  const bool quad = kd->kind != CHD_KERNEL_LINEAR;
+  int nblk = 0;
+  if (quad) {
+    const int nt = (N + 31) / 32;
+    gmat_kernel<<<dim3(nt, nt, T), 256, 0, st>>>(X, n, N, yb, Gm);
+    CHD_LAUNCHED();
+    quad_rows_kernel<<<dim3((N + 7) / 8, T), 256, 0, st>>>(Gm, N, w, cluster_of, rowq);
+    CHD_LAUNCHED();
+  }
+  if (kd->kind == CHD_KERNEL_GAUSSIAN) {
+    transpose_kernel<<<dim3((n + 31) / 32, (N + 31) / 32), 256, 0, st>>>(X, n, N, XT);
+    CHD_LAUNCHED();
+    const int tb = (n + GA_TILE - 1) / GA_TILE;
+    const int ntiles = tb * (tb + 1) / 2;
+    nblk = ntiles < GA_BLOCKS ? ntiles : GA_BLOCKS;
+    const size_t smem = (size_t)C * 8 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      CHD_CUDA(cudaFuncSetAttribute(gauss_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)pl->smem_optin));
+      attr_set = true;
+    }
+    gauss_pairs_kernel<<<dim3(nblk, T), 256, smem, st>>>(XT, n, N, C, yb, w, mem_off, mem_idx,
+                                                         1.0 / (2.0 * kd->l * kd->l), gpart, nblk);
+    CHD_LAUNCHED();
+  }
+  act_finalize_kernel<<<T, 256, 0, st>>>(*kd, N, C, w, mem_off, mem_idx, gdot, quad ? rowq : nullptr, gpart, nblk,
+                                         energy, alive, act, act_stride, prune, pruned, pruned_stride);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+}  // namespace chd
+
+extern "C" int chd_activations(const chd_plan* plan, const chd_kernel_desc* kd, const double* X,
+                               const int32_t* cluster_of, const uint8_t* w0, uint8_t* alive, const double* yb,
+                               const double* ga, int T, double* act, int prune, int32_t* pruned, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  const chd::Plan* pl = (const chd::Plan*)plan;
+  if (!pl || !kd || !X || !cluster_of || !w0 || !alive || !yb || !ga || !act || T <= 0) return CHD_EINVAL;
+  if (prune && !pruned) return CHD_EINVAL;
+  return chd::act_launch(pl, kd, X, cluster_of, w0, alive, yb, ga, T, act, (size_t)pl->C, prune, pruned, 1, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,283 @@
+// C-ABI entry points: plan, workspace carving, the fused regression and the device-resident
+// prune chain (include/chd_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "internal.cuh"
+
+namespace chd {
+
+std::atomic<unsigned long long> g_launches{0};
+static char g_err[1024] = "";
+static std::mutex g_err_mu;
+
+void set_error(const char* fmt, ...) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int ZLD = CHD_Z_SAMPLES;  // leading dimension of the Z-test block
+
+struct RegressBuffers {
+  uint32_t* subkeys;
+  double *B, *d, *e, *beta0, *loss, *eta, *uu, *x;
+  TridiagBuffers tb;
+};
+
+static size_t regress_workspace(const Plan* pl, int T) {
+  const size_t n = pl->n;
+  size_t b = 0;
+  b += align_up(T * 2 * sizeof(uint32_t), 256);
+  b += align_up(T * n * ZLD * sizeof(double), 256);
+  b += 5 * align_up(T * n * sizeof(double), 256);
+  b += align_up(T * sizeof(double), 256);
+  b += align_up((size_t)T * CHD_GRID_POINTS * sizeof(double), 256);
+  return b + tridiag_workspace(pl, T) + 4096;
+}
+
+static bool regress_carve(const Plan* pl, int T, Carver& cv, RegressBuffers& rb) {
+  const size_t n = pl->n;
+  rb.subkeys = cv.take<uint32_t>((size_t)T * 2);
+  rb.B = cv.take<double>(T * n * ZLD);
+  rb.d = cv.take<double>(T * n);
+  rb.e = cv.take<double>(T * n);
+  rb.eta = cv.take<double>(T * n);
+  rb.uu = cv.take<double>(T * n);
+  rb.x = cv.take<double>(T * n);
+  rb.beta0 = cv.take<double>(T);
+  rb.loss = cv.take<double>((size_t)T * CHD_GRID_POINTS);
+  return tridiag_carve(pl, T, cv, rb.tb) && cv.ok;
+}
+
+// key split -> Z samples -> tridiagonalisation (+ Q^T S) -> gamma / solve / Z-test -> yb = -beta0 Q x
+static int regress_core(const Plan* pl, double* K, int ldk, const double* ga, int T, const double* grid,
+                        int gamma_min_mode, double gamma_min_base, double* gamma_min, const uint32_t* keys,
+                        uint32_t* keys_out, int want_lambda_min, double* lambda_min, double* yb, size_t yb_stride,
+                        double* noise, double* z_low, double* z_high, double* gamma, size_t out_stride,
+                        int32_t* status, const RegressBuffers& rb, cudaStream_t st) {
+  int rc;
+  if ((rc = chd_split(keys, T, keys_out, rb.subkeys, st))) return rc;
+  if ((rc = chd_normal(rb.subkeys, T, pl->n, CHD_Z_SAMPLES, rb.B, ZLD, st))) return rc;
+  if ((rc = tridiag_launch(pl, K, ldk, ga, T, rb.B, ZLD, CHD_Z_SAMPLES, rb.d, rb.e, rb.beta0, rb.tb, st))) return rc;
+  if ((rc = gamma_launch(pl, rb.d, rb.e, rb.beta0, grid, rb.loss, rb.B, ZLD, CHD_Z_SAMPLES, gamma_min_mode,
+                         gamma_min_base, gamma_min, want_lambda_min, lambda_min, rb.eta, rb.uu, rb.x, noise, z_low,
+                         z_high, gamma, out_stride, status, T, st)))
+    return rc;
+  return backtransform_launch(pl, K, ldk, rb.tb, rb.x, rb.beta0, yb, yb_stride, T, st);
+}
+
+__global__ void refresh_gamma_min_kernel(const double* __restrict__ lambda_min, double* __restrict__ gamma_min,
+                                         int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) {
+    const double l = lambda_min[t];
+    gamma_min[t] = (l + 1e-9 < 0.0) ? -2.0 * l : 1e-9;   // _GraphDiscoveryMain.py:628-631
+  }
+}
+
+__global__ void dmma_peak_kernel(int iters, double* sink) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace chd
+
+using namespace chd;
+
+extern "C" const char* chd_version(void) { return "chd_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* chd_last_error(void) { return g_err; }
+extern "C" unsigned long long chd_launch_count(void) { return g_launches.load(); }
+
+extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device, int ctas_per_matrix) {
+  if (!plan || n < 2 || N < 1 || C < 1) return CHD_EINVAL;
+  cudaDeviceProp prop;
+  CHD_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("chd_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return CHD_EINVAL;
+  }
+  Plan* pl = new Plan();
+  pl->n = n; pl->N = N; pl->C = C; pl->device = device;
+  pl->sm_count = prop.multiProcessorCount;
+  pl->smem_optin = prop.sharedMemPerBlockOptin;
+  pl->nb = 32;
+  pl->rows_per_chunk = 16;
+  int G = ctas_per_matrix;
+  if (G <= 0) {
+    if (n <= 256) G = 2;
+    else if (n <= 640) G = 4;
+    else if (n <= 1536) G = 8;
+    else if (n <= 3072) G = 18;
+    else if (n <= 6144) G = 37;
+    else G = 74;
+  }
+  if (G > pl->sm_count) G = pl->sm_count;
+  pl->G = G;
+  while (tridiag_smem_bytes(pl) > pl->smem_optin && pl->G < pl->sm_count) pl->G += 1;
+  if (tridiag_smem_bytes(pl) > pl->smem_optin) {
+    set_error("n=%d does not fit the tridiagonalisation's shared memory even with %d CTAs", n, pl->G);
+    delete pl;
+    return CHD_EINVAL;
+  }
+  pl->wave = pl->sm_count / pl->G;
+  if (pl->wave < 1) pl->wave = 1;
+  *plan = (chd_plan*)pl;
+  return CHD_OK;
+}
+
+extern "C" void chd_plan_destroy(chd_plan* plan) { delete (Plan*)plan; }
+
+extern "C" int chd_plan_info(const chd_plan* plan, int* ctas_per_matrix, int* matrices_per_wave, int* sm_count) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl) return CHD_EINVAL;
+  if (ctas_per_matrix) *ctas_per_matrix = pl->G;
+  if (matrices_per_wave) *matrices_per_wave = pl->wave;
+  if (sm_count) *sm_count = pl->sm_count;
+  return CHD_OK;
+}
+
+extern "C" size_t chd_workspace_bytes(const chd_plan* plan, int T) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || T <= 0) return 0;
+  const size_t n = pl->n;
+  const size_t ldk = align_up(n, 2);
+  size_t gb = 0;
+  gram_workspace(pl, T, -1, &gb);
+  size_t b = regress_workspace(pl, T);
+  b += align_up(T * n * ldk * sizeof(double), 256);  // K work matrices (prune chain)
+  b += align_up((size_t)T * pl->N, 256);             // active variable masks
+  b += gb + act_workspace(pl, T);
+  return b + 8192;
+}
+
+extern "C" int chd_regress(const chd_plan* plan, double* K, int ldk, const double* ga, int T,
+                           const double* gamma_grid, int gamma_min_mode, double gamma_min_base, double* gamma_min,
+                           const uint32_t* keys, double* yb, double* noise, double* z_low, double* z_high,
+                           double* gamma, uint32_t* keys_out, double* lambda_min, int32_t* status, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !K || !ga || !gamma_grid || !gamma_min || !keys || !yb || !noise || !z_low || !z_high || !gamma ||
+      !keys_out || !status || T <= 0 || ldk < pl->n || (ldk & 1))
+    return CHD_EINVAL;
+  Carver cv(workspace, workspace_bytes);
+  RegressBuffers rb;
+  if (!regress_carve(pl, T, cv, rb)) {
+    set_error("chd_regress: workspace too small (%zu needed, %zu given)", cv.off, workspace_bytes);
+    return CHD_ENOSPC;
+  }
+  return regress_core(pl, K, ldk, ga, T, gamma_grid, gamma_min_mode, gamma_min_base, gamma_min, keys, keys_out,
+                      lambda_min != nullptr, lambda_min, yb, (size_t)pl->n, noise, z_low, z_high, gamma, 1, status, rb,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int chd_tridiag(const chd_plan* plan, double* K, int ldk, const double* ga, int T, double* B, int ldb,
+                           int nb_cols, double* d, double* e, double* beta0, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !K || !ga || !d || !e || !beta0 || T <= 0 || ldk < pl->n || (ldk & 1)) return CHD_EINVAL;
+  Carver cv(workspace, workspace_bytes);
+  TridiagBuffers tb;
+  if (!tridiag_carve(pl, T, cv, tb)) return CHD_ENOSPC;
+  return tridiag_launch(pl, K, ldk, ga, T, B, ldb, B ? nb_cols : 0, d, e, beta0, tb, (cudaStream_t)stream);
+}
+
+extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, const double* X,
+                               const int32_t* cluster_of, const uint8_t* w0, uint8_t* alive, const double* ga,
+                               double* yb, uint32_t* keys, const double* gamma_grid, double* lambda_min,
+                               double* gamma_min, int T, int first_step, int steps, int32_t* pruned, double* noise,
+                               double* z_low, double* z_high, double* gamma, double* act, double* yb_chain,
+                               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !kd || !X || !cluster_of || !w0 || !alive || !ga || !yb || !keys || !gamma_grid || !lambda_min ||
+      !gamma_min || T <= 0 || steps < 0 || !pruned || !noise || !z_low || !z_high || !gamma || !act || !status)
+    return CHD_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = pl->n, N = pl->N, C = pl->C;
+  const int ldk = (int)align_up(n, 2);
+  Carver cv(workspace, workspace_bytes);
+  RegressBuffers rb;
+  bool ok = regress_carve(pl, T, cv, rb);
+  double* K = cv.take<double>((size_t)T * n * ldk);
+  uint8_t* w = cv.take<uint8_t>((size_t)T * N);
+  size_t gb = 0;
+  gram_workspace(pl, T, -1, &gb);
+  char* gws = cv.take<char>(gb);
+  const size_t ab = act_workspace(pl, T);
+  char* aws = cv.take<char>(ab);
+  if (!ok || !cv.ok) {
+    set_error("chd_prune_chain: workspace too small (%zu needed, %zu given)", cv.off, workspace_bytes);
+    return CHD_ENOSPC;
+  }
+  if (ldk > n) CHD_CUDA(cudaMemsetAsync(K, 0, (size_t)T * n * ldk * sizeof(double), st));
+  int rc;
+  for (int s = 0; s < steps; ++s) {
+    const long long step = (long long)first_step + s;
+    const long long p = (long long)N - step - 1;
+    auto is_refresh = [&](long long stp) {
+      const long long pp = (long long)N - stp - 1;
+      return (stp % 50 == 0) || (pp * (pp + 1) == 2LL * N);
+    };
+    (void)p;
+    if (is_refresh(step)) {
+      refresh_gamma_min_kernel<<<(T + 127) / 128, 128, 0, st>>>(lambda_min, gamma_min, T);
+      CHD_LAUNCHED();
+    }
+    if ((rc = act_launch(pl, kd, X, cluster_of, w0, alive, yb, ga, T, act + (size_t)s * C, (size_t)steps * C, 1,
+                         pruned + s, (size_t)steps, aws, ab, st)))
+      return rc;
+    if ((rc = active_vars_launch(w0, alive, cluster_of, N, C, T, w, st))) return rc;
+    if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st))) return rc;
+    if ((rc = regress_core(pl, K, ldk, ga, T, gamma_grid, 0, 0.0, gamma_min, keys, keys, is_refresh(step + 1),
+                           lambda_min, yb, (size_t)n, noise + s, z_low + s, z_high + s, gamma + s, (size_t)steps,
+                           status, rb, st)))
+      return rc;
+    if (yb_chain)
+      CHD_CUDA(cudaMemcpy2DAsync(yb_chain + (size_t)s * n, (size_t)steps * n * sizeof(double), yb,
+                                 (size_t)n * sizeof(double), (size_t)n * sizeof(double), T,
+                                 cudaMemcpyDeviceToDevice, st));
+  }
+  return CHD_OK;
+}
+
+extern "C" int chd_dmma_peak(int iters, double* tflops) {
+  if (iters <= 0 || !tflops) return CHD_EINVAL;
+  int dev = 0;
+  CHD_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CHD_CUDA(cudaGetDeviceProperties(&prop, dev));
+  double* sink;
+  CHD_CUDA(cudaMalloc(&sink, 8));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256;
+  dmma_peak_kernel<<<blocks, threads>>>(iters / 10 + 1, sink);  // warm-up
+  cudaEvent_t e0, e1;
+  CHD_CUDA(cudaEventCreate(&e0));
+  CHD_CUDA(cudaEventCreate(&e1));
+  CHD_CUDA(cudaEventRecord(e0));
+  dmma_peak_kernel<<<blocks, threads>>>(iters, sink);
+  CHD_CUDA(cudaEventRecord(e1));
+  CHD_CUDA(cudaEventSynchronize(e1));
+  g_launches.fetch_add(2);
+  float ms = 0;
+  CHD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const double flops = (double)blocks * (threads / 32) * (double)iters * 8.0 * 512.0;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return CHD_OK;
+}

@@ -1,0 +1,35 @@
+// Internal cross-translation-unit declarations of libchd_b200.
+#pragma once
+#include "common.cuh"
+
+namespace chd {
+
+struct TridiagBuffers {
+  double *tau, *v0, *u, *Vp, *Wp, *Wraw, *part, *pgram;
+  unsigned* bar;
+};
+
+size_t tridiag_smem_bytes(const Plan* pl);
+size_t tridiag_workspace(const Plan* pl, int T);
+bool tridiag_carve(const Plan* pl, int T, Carver& cv, TridiagBuffers& tb);
+int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nbc,
+                   double* d, double* e, double* beta0, const TridiagBuffers& tb, cudaStream_t st);
+int backtransform_launch(const Plan* pl, const double* K, int ldk, const TridiagBuffers& tb, const double* x,
+                         const double* beta0, double* out, size_t out_stride, int T, cudaStream_t st);
+int gamma_launch(const Plan* pl, const double* d, const double* e, const double* beta0, const double* grid,
+                 double* loss, double* B, int ldb, int nz, int gamma_min_mode, double gamma_min_base,
+                 double* gamma_min, int want_lambda_min, double* lambda_min, double* eta, double* uu, double* x,
+                 double* noise, double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status,
+                 int T, cudaStream_t st);
+int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes);
+int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
+                const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t act_workspace(const Plan* pl, int T);
+int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const int32_t* cluster_of,
+               const uint8_t* w0, uint8_t* alive, const double* yb, const double* ga, int T, double* act,
+               size_t act_stride, int prune, int32_t* pruned, size_t pruned_stride, void* ws, size_t ws_bytes,
+               cudaStream_t st);
+int active_vars_launch(const uint8_t* w0, const uint8_t* alive, const int32_t* cluster_of, int N, int C, int T,
+                       uint8_t* w, cudaStream_t st);
+
+}  // namespace chd
