@@ -51,6 +51,8 @@ _SIGNATURES = {
     "chd_predict": (_i, [_vp, ctypes.POINTER(KernelDesc), _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "chd_tridiag": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "chd_dmma_peak": (_i, [_i, ctypes.POINTER(_d)]),
+    "chd_profile_enable": (_i, [_i]),
+    "chd_profile_read": (_i, [ctypes.POINTER(_d), ctypes.POINTER(_i)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -241,6 +243,17 @@ class Plan:
         _check(load().chd_predict(self._h, ctypes.byref(desc), _ptr(X), _ptr(Xq), nq, _ptr(w), _ptr(yb), T, _ptr(out),
                                   _ptr(ws), ws.numel(), _stream()), "chd_predict")
         return out
+
+
+def profile_enable(on=True):
+    _check(load().chd_profile_enable(int(bool(on))), "chd_profile_enable")
+
+
+def profile_read():
+    """(total ms, launches) of the tridiagonalisation kernel since profile_enable(True)."""
+    ms, cnt = ctypes.c_double(), ctypes.c_int()
+    _check(load().chd_profile_read(ctypes.byref(ms), ctypes.byref(cnt)), "chd_profile_read")
+    return ms.value, cnt.value
 
 
 def dmma_peak_tflops(iters=20000):

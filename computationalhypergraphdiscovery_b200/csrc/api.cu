@@ -254,6 +254,9 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
   return CHD_OK;
 }
 
+extern "C" int chd_profile_enable(int on) { return profile_enable(on); }
+extern "C" int chd_profile_read(double* total_ms, int* launches) { return profile_read(total_ms, launches); }
+
 extern "C" int chd_dmma_peak(int iters, double* tflops) {
   if (iters <= 0 || !tflops) return CHD_EINVAL;
   int dev = 0;

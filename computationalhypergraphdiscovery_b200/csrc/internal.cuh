@@ -29,6 +29,8 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
                const uint8_t* w0, uint8_t* alive, const double* yb, const double* ga, int T, double* act,
                size_t act_stride, int prune, int32_t* pruned, size_t pruned_stride, void* ws, size_t ws_bytes,
                cudaStream_t st);
+int profile_enable(int on);
+int profile_read(double* total_ms, int* launches);
 int active_vars_launch(const uint8_t* w0, const uint8_t* alive, const int32_t* cluster_of, int N, int C, int T,
                        uint8_t* w, cudaStream_t st);
 

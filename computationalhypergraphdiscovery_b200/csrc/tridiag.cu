@@ -11,7 +11,8 @@
 // FP64 tensor cores (DMMA m8n8k4).  The matrix is stored full (both triangles) so that every row
 // slice is owned by exactly one CTA and the mat-vec needs no cross-CTA reduction.  The Z-test
 // block B (n x 100) is transformed on the fly (B <- H_c B) inside the same three phases.
-#include <cooperative_groups.h>
+#include <utility>
+#include <vector>
 
 #include "internal.cuh"
 
@@ -493,6 +494,29 @@ __global__ void __launch_bounds__(512) backtransform_kernel(BackArgs a) {
 }
 
 // ------------------------------------------------------------------ host side
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+
+int profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  return CHD_OK;
+}
+
+int profile_read(double* total_ms, int* launches) {
+  double tot = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    CHD_CUDA(cudaEventSynchronize(g_prof_events[i].second));
+    float ms = 0.f;
+    CHD_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)g_prof_used;
+  return CHD_OK;
+}
+
 size_t tridiag_smem_bytes(const Plan* pl) {
   const int chunks = (pl->n + TD_RB - 1) / TD_RB;
   const int LR = (chunks + pl->G - 1) / pl->G * TD_RB;
@@ -565,8 +589,21 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
     b.pgram = tb.pgram + (size_t)t0 * n * pl->nb;
     b.bar = tb.bar + t0;
     void* params[] = {&b};
+    if (g_prof_on) {
+      if (g_prof_used == g_prof_events.size()) {
+        cudaEvent_t e0, e1;
+        CHD_CUDA(cudaEventCreate(&e0));
+        CHD_CUDA(cudaEventCreate(&e1));
+        g_prof_events.emplace_back(e0, e1);
+      }
+      CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].first, st));
+    }
     CHD_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(pl->G, cnt), dim3(TD_THREADS), params, smem, st));
     g_launches.fetch_add(1);
+    if (g_prof_on) {
+      CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].second, st));
+      ++g_prof_used;
+    }
   }
   return CHD_OK;
 }

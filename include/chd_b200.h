@@ -136,6 +136,11 @@ int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, const double* X
  * B (T x n x ldb, may be NULL, nb_cols columns) is overwritten with Q^T B. Reflectors stay in K. */
 int chd_tridiag(const chd_plan* plan, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nb_cols,
                 double* d, double* e, double* beta0, void* workspace, size_t workspace_bytes, void* stream);
+/* Optional timing of the dominant kernel: when enabled, every tridiagonalisation launch is bracketed by
+ * cudaEvents on its own stream; chd_profile_read synchronises those events and returns the summed duration
+ * (ms) and the number of launches since the last chd_profile_enable(1). */
+int chd_profile_enable(int on);
+int chd_profile_read(double* total_ms, int* launches);
 /* FP64 tensor-core (DMMA) throughput probe: runs `iters` back-to-back m8n8k4 chains per warp on
  * the whole GPU and returns the measured TFLOP/s (host-synchronising; used for the roofline peak). */
 int chd_dmma_peak(int iters, double* tflops);

@@ -16,7 +16,7 @@ Follows HELP (helper_functions.py), MAIN (_GraphDiscoveryMain.py), CONT
 import numpy as np
 
 from . import jaxprng
-from .kernels import make_specs, gram, individual_influence, linear_core
+from .kernels import make_specs, gram, individual_influence, linear_core, make_exps
 from .regression import perform_regression_and_find_gamma
 
 
@@ -51,7 +51,7 @@ def initial_masks(index_matrix, target_indexes, adjacency=None):
 
 
 # --------------------------------------------------------------------- activations
-def activations(spec, X, yb, ga, active_modes, has_clusters):
+def activations(spec, X, yb, ga, active_modes, has_clusters, exps=None):
     """make_activation_function HELP:40-134."""
     energy = -np.dot(ga, yb)
     empty = np.all(active_modes == 0, axis=1)
@@ -75,7 +75,7 @@ def activations(spec, X, yb, ga, active_modes, has_clusters):
             if empty[c]:
                 act[c] = 0.0
                 continue
-            M = individual_influence(spec, X, X, w, active_modes[c])
+            M = individual_influence(spec, X, X, w, active_modes[c], exps)
             act[c] = np.dot(yb, M @ yb)
         act = act / energy
     return np.where(empty, 2.0, act)
@@ -86,19 +86,19 @@ def _argmin_nanfirst(a):
     return int(np.argmax(nan)) if nan.any() else int(np.argmin(a))
 
 
-def prune_step(spec, X, active_modes, ga, yb, key, gamma_min, has_clusters):
+def prune_step(spec, X, active_modes, ga, yb, key, gamma_min, has_clusters, exps=None):
     """make_find_ancestor_function.step HELP:166-176."""
-    act = activations(spec, X, yb, ga, active_modes, has_clusters)
+    act = activations(spec, X, yb, ga, active_modes, has_clusters, exps)
     j = _argmin_nanfirst(act)
     active_modes = active_modes.copy()
     active_modes[j, :] = 0.0
-    K = gram(spec, X, X, np.sum(active_modes, axis=0))
+    K = gram(spec, X, X, np.sum(active_modes, axis=0), exps)
     yb, noise, zl, zh, gamma, key = perform_regression_and_find_gamma(K, ga, gamma_min, key)
     return active_modes, yb, gamma, key, act, noise, zl, zh
 
 
 # -------------------------------------------------------------------------- stage 1
-def kernel_performance(specs, X, active_modess, gas, subkeys, gamma_min):
+def kernel_performance(specs, X, active_modess, gas, subkeys, gamma_min, caches=None):
     """get_kernel_performance MAIN:448-511. Returns dict of arrays (T, nk, ...)
     plus the stage-1 minimum eigenvalues (T, nk)."""
     T, nk, n = gas.shape[0], len(specs), X.shape[0]
@@ -111,7 +111,7 @@ def kernel_performance(specs, X, active_modess, gas, subkeys, gamma_min):
     mineig = np.zeros((T, nk))
     for k, spec in enumerate(specs):
         for t in range(T):
-            K = gram(spec, X, X, np.sum(active_modess[t], axis=0))
+            K = gram(spec, X, X, np.sum(active_modess[t], axis=0), (caches or {}).get(spec.name))
             me = np.linalg.eigvalsh(K)[0]
             mineig[t, k] = me
             gm = -2 * me if me + gamma_min < 0 else gamma_min           # MAIN:477-479
@@ -167,7 +167,7 @@ def anomaly_clamp(a):
 
 # -------------------------------------------------------------------------- stage 2
 def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, zhi,
-                    loop_number, has_clusters):
+                    loop_number, has_clusters, exps=None):
     """prune_ancestors MAIN:559-701 for the targets that chose `spec`."""
     Tk = gas.shape[0]
     N = X.shape[1]
@@ -181,7 +181,7 @@ def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, 
     def refresh():
         out = np.empty(Tk)
         for t in range(Tk):
-            me = np.linalg.eigvalsh(gram(spec, X, X, np.sum(active[t], axis=0)))[0]
+            me = np.linalg.eigvalsh(gram(spec, X, X, np.sum(active[t], axis=0), exps))[0]
             out[t] = -2 * me if me + 1e-9 < 0 else 1e-9                 # MAIN:628-631
         return out
 
@@ -197,7 +197,7 @@ def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, 
         h = np.empty(Tk)
         for t in range(Tk):
             (a_new[t], yb_new[t], g_new[t], k_new[t], act[t], nz[t], l[t], h[t]) = prune_step(
-                spec, X, active[t], gas[t], ybs[t], keys[t], gamma_min_kernel[t], has_clusters)
+                spec, X, active[t], gas[t], ybs[t], keys[t], gamma_min_kernel[t], has_clusters, exps)
         active, ybs, keys = a_new, yb_new, k_new
         return g_new, act, nz, l, h
 
@@ -258,7 +258,12 @@ def fit(X, names, kernels=None, normalize_data=True, clusters=None, adjacency=No
         key = jaxprng.PRNGKey(0)
     subkeys = jaxprng.split(key, len(targets) + 1)[1:]                  # MAIN:311-313
 
-    perf = kernel_performance(specs, X, active0, gas, subkeys, gamma_min)
+    # the reference caches exps (n x n x N) in GaussianMode.setup (KERN:307-309); do so when it fits
+    caches = {}
+    for spec in specs:
+        if spec.name == "gaussian" and X.shape[0] ** 2 * X.shape[1] * 8 <= 1.5e9:
+            caches["gaussian"] = make_exps(X, spec.l)
+    perf = kernel_performance(specs, X, active0, gas, subkeys, gamma_min, caches)
     T = len(targets)
     chosen = np.empty(T, dtype=int)
     sel = np.empty(T, dtype=int)
@@ -278,7 +283,7 @@ def fit(X, names, kernels=None, normalize_data=True, clusters=None, adjacency=No
         if not mask.any():
             continue
         ch = prune_ancestors(spec, X, active0[mask], gas[mask], ybs[mask], gammas[mask], skeys[mask],
-                             noises[mask], zlo[mask], zhi[mask], C - 2, has_clusters)
+                             noises[mask], zlo[mask], zhi[mask], C - 2, has_clusters, caches.get(spec.name))
         ch["noises"] = anomaly_clamp(ch["noises"])
         ch["Z_lows"] = anomaly_clamp(ch["Z_lows"])
         ch["Z_highs"] = anomaly_clamp(ch["Z_highs"])

@@ -62,8 +62,17 @@ def quad_from_core(L, scale, alpha):
     return scale * (alpha + L) ** 2 + (1 - alpha ** 2 * scale)
 
 
-def gaussian_product(X, Y, w, l):
-    """prod_d (1 + w_d * exp(-(x_d - y_d)^2 / (2 l^2)))  (KERN:253-255)."""
+def make_exps(X, l):
+    """GaussianMode.setup's cached tensor exps[j, i, d] (KERN:307-309; symmetric in i, j for X = Y)."""
+    diff = X[:, None, :] - X[None, :, :]
+    return np.exp(-(diff ** 2) / (2 * l ** 2))
+
+
+def gaussian_product(X, Y, w, l, exps=None):
+    """prod_d (1 + w_d * exp(-(x_d - y_d)^2 / (2 l^2)))  (KERN:253-255).  With the reference's cached
+    `exps` the product runs over all N dims (mask by multiply) exactly as the reference does."""
+    if exps is not None:
+        return np.prod(1.0 + w[None, None, :] * exps, axis=2)
     P = np.ones((X.shape[0], Y.shape[0]))
     inv = 1.0 / (2 * l ** 2)
     for d in np.nonzero(w)[0]:
@@ -72,8 +81,8 @@ def gaussian_product(X, Y, w, l):
     return P
 
 
-def gram(spec, X, Y, w):
-    """kernel(X, Y, which_dim)  (ModeKernel.__call__ KERN:58-59)."""
+def gram(spec, X, Y, w, exps=None):
+    """kernel(X, Y, which_dim)  (ModeKernel.__call__ KERN:58-59).  `exps`: optional cache (X is Y)."""
     w = np.asarray(w, dtype=np.float64)
     L = linear_core(X, Y, w)
     if spec.name == "linear":
@@ -81,7 +90,7 @@ def gram(spec, X, Y, w):
     if spec.name == "quadratic":
         return quad_from_core(L, spec.scale, spec.alpha)
     if spec.name == "gaussian":
-        return (spec.scale * gaussian_product(X, Y, w, spec.l)
+        return (spec.scale * gaussian_product(X, Y, w, spec.l, exps)
                 + quad_from_core(L, spec.quad_scale, spec.alpha) - 1)
     raise ValueError(spec.name)
 
@@ -93,7 +102,7 @@ def _quad_influence(X, Y, w, w_only, scale, alpha):
     return scale * (alpha + lin_only) ** 2 + 2 * scale * lin_only * lin_rest - scale * alpha ** 2
 
 
-def individual_influence(spec, X, Y, w, w_only):
+def individual_influence(spec, X, Y, w, w_only, exps=None):
     """individual_influence(X, Y, which_dim, which_dim_only) KERN:125-141,
     211-228, 319-334."""
     w = np.asarray(w, dtype=np.float64)
@@ -104,8 +113,8 @@ def individual_influence(spec, X, Y, w, w_only):
         return _quad_influence(X, Y, w, w_only, spec.scale, spec.alpha)  # KERN:175-185
     if spec.name == "gaussian":                                  # KERN:270-278
         rest = w * (1 - w_only)
-        only_part = gaussian_product(X, Y, w_only, spec.l) - 1
-        rest_part = gaussian_product(X, Y, rest, spec.l)
+        only_part = gaussian_product(X, Y, w_only, spec.l, exps) - 1
+        rest_part = gaussian_product(X, Y, rest, spec.l, exps)
         return (_quad_influence(X, Y, w, w_only, spec.quad_scale, spec.alpha)
                 + spec.scale * only_part * rest_part)
     raise ValueError(spec.name)
