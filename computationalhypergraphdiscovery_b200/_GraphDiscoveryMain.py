@@ -27,6 +27,7 @@ import torch
 
 from . import _native
 from . import random as chd_random
+from . import parallel
 from .Modes import ModeContainer, LinearMode, QuadraticMode, GaussianMode
 from .decision import *  # noqa: F401,F403  (reference does the same, MAIN:14)
 from .decision import MinNoiseKernelChooser, MaxIncrementModeChooser
@@ -179,15 +180,28 @@ class GraphDiscovery:
         key = np.asarray(key, dtype=np.uint32)
         if targets is None:
             targets = self.names
-        targets = list(targets)
+        all_targets = list(targets)
+        subkeys_all = chd_random.split(key, len(all_targets) + 1)[1:]   # MAIN:311-313
+        # multi-GPU: ranks take disjoint blocks of targets (parallel.py); every target keeps the subkey it
+        # has in the unsharded run, so results do not depend on the number of GPUs
+        rank, world = parallel.dist_info()
+        targets = parallel.shard_targets(all_targets, rank, world)
+        pos = {name: i for i, name in enumerate(all_targets)}
+        subkeys = subkeys_all[[pos[t] for t in targets]] if targets else subkeys_all[:0]
         gas_idx, w0 = self._prepare_modes_for_ancestor_finding(targets)
-        subkeys = chd_random.split(key, len(targets) + 1)[1:]        # MAIN:311-313
 
         kernel_performance, stage1_dev = self.get_kernel_performance(w0, gas_idx, subkeys)
         ybs, gammas, subkeys, noisess, Z_lows, Z_highs, chosen_kernels = GraphDiscovery.choose_kernel(
             kernel_performance, kernel_chooser)
 
         self.last_fit = dict(targets=targets, stage1=kernel_performance, chosen_kernel=chosen_kernels, chains={})
+        # the chain length is a property of the kernel group over ALL targets (quirk C-16, MAIN:659-660)
+        im = self.modes.index_matrix
+        rows0 = ((im[None, :, :] * w0[:, None, :]).sum(axis=2) > 0).sum(axis=1) if len(targets) else np.zeros(0, int)
+        group_rows = [int(rows0[chosen_kernels == i].max()) if np.any(chosen_kernels == i) else -1
+                      for i in range(len(self.kernels))]
+        if world > 1:
+            group_rows = [max(v) for v in zip(*parallel.all_gather_list(group_rows))]
         for i, kernel in enumerate(self.kernels):
             mask_kernel = chosen_kernels == i
             if not np.any(mask_kernel):
@@ -198,7 +212,7 @@ class GraphDiscovery:
                 gammas_kernel=gammas[mask_kernel], subkeys_kernel=subkeys[mask_kernel],
                 noise_kernel=noisess[mask_kernel], Z_low_kernel=Z_lows[mask_kernel],
                 Z_high_kernel=Z_highs[mask_kernel], lambda_min_kernel=stage1_dev["lambda_min"][mask_kernel, i],
-                loop_number=len(self.modes.clusters) - 2, message=message)
+                loop_number=len(self.modes.clusters) - 2, message=message, group_max_rows=group_rows[i])
             raw_noises = noisess_kernel
             noisess_kernel, Z_lows_kernel, Z_highs_kernel = self._anomaly_clamp(
                 noisess_kernel, Z_lows_kernel, Z_highs_kernel)
@@ -213,6 +227,9 @@ class GraphDiscovery:
                                  Z_lows_kernel, Z_highs_kernel, activationss_kernel, kernel_performance,
                                  gammas_kernel, ybs_kernel)
         self.process_results(targets, -1, chosen_kernels == -1, *([None] * 6), kernel_performance, None, None)
+        if world > 1:   # one all-gather of the per-node results
+            merged = parallel.all_gather_results(parallel.export_node_results(self.G, targets))
+            parallel.merge_node_results(self.G, merged)
 
     @staticmethod
     def _anomaly_clamp(noises, zl, zh):
@@ -313,7 +330,8 @@ class GraphDiscovery:
 
     # ------------------------------------------------------------------ stage 2
     def prune_ancestors(self, kernel, X, gas_idx, w0, ybs_kernel, gammas_kernel, subkeys_kernel, noise_kernel,
-                        Z_low_kernel, Z_high_kernel, lambda_min_kernel, loop_number, message):
+                        Z_low_kernel, Z_high_kernel, lambda_min_kernel, loop_number, message,
+                        group_max_rows=None):
         """Backward elimination for the targets that chose `kernel` (MAIN:559-701).  All targets of
         the group step in lock-step (quirk: the loop only stops when every mask is empty,
         MAIN:659-660); the steps run device-resident in chd_prune_chain.  Returns the reference's
@@ -328,6 +346,8 @@ class GraphDiscovery:
         # number of non-empty rows per target decides when every mask is empty
         nonempty0 = ((im[None, :, :] * w0[:, None, :]).sum(axis=2) > 0)
         max_rows = int(nonempty0.sum(axis=1).max()) if Tk else 0
+        if group_max_rows is not None:
+            max_rows = max(max_rows, int(group_max_rows))
         steps_planned = min(loop_number, max_rows) if loop_number > 0 else 0
         self.print_func(f"Finding ancestors with kernel [{kernel}]: {steps_planned} steps x {Tk} targets {message}")
 
