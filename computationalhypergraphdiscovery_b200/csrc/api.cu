@@ -123,13 +123,20 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
     else if (n <= 640) G = 4;
     else if (n <= 1536) G = 8;
     else if (n <= 3072) G = 18;
-    else if (n <= 6144) G = 37;
+    else if (n <= 8192) G = 37;
     else G = 74;
   }
   if (G > pl->sm_count) G = pl->sm_count;
   pl->G = G;
-  while (tridiag_smem_bytes(pl) > pl->smem_optin && pl->G < pl->sm_count) pl->G += 1;
-  if (tridiag_smem_bytes(pl) > pl->smem_optin) {
+  // panel width 32 if the CTA's panel slice fits in shared memory, else 16, else more CTAs per matrix
+  auto fits = [&]() {
+    pl->nb = 32;
+    if (tridiag_smem_bytes(pl) <= pl->smem_optin) return true;
+    pl->nb = 16;
+    return tridiag_smem_bytes(pl) <= pl->smem_optin;
+  };
+  while (!fits() && pl->G < pl->sm_count) pl->G += 1;
+  if (!fits()) {
     set_error("n=%d does not fit the tridiagonalisation's shared memory even with %d CTAs", n, pl->G);
     delete pl;
     return CHD_EINVAL;

@@ -5,7 +5,7 @@
 namespace chd {
 
 struct TridiagBuffers {
-  double *tau, *v0, *u, *Vp, *Wp, *Wraw, *part, *pgram;
+  double *tau, *v0, *u, *rsum, *Vp, *Wp, *colpart, *part, *pgram;
   unsigned* bar;
 };
 

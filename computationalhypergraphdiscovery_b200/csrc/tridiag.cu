@@ -11,6 +11,7 @@
 // FP64 tensor cores (DMMA m8n8k4).  The matrix is stored full (both triangles) so that every row
 // slice is owned by exactly one CTA and the mat-vec needs no cross-CTA reduction.  The Z-test
 // block B (n x 100) is transformed on the fly (B <- H_c B) inside the same three phases.
+#include <stdlib.h>
 #include <utility>
 #include <vector>
 
@@ -22,7 +23,8 @@ constexpr int TD_THREADS = 512;
 constexpr int TD_RB = 16;         // rows per ownership chunk (= warps per CTA)
 constexpr int TD_MAXNB = 32;      // panel width
 constexpr int TD_BC = 128;        // max columns of B
-constexpr int TD_TILE = 64;       // syr2k tile
+constexpr int TD_TILE = 128;      // syr2k tile (TD_TILE x TD_TILE, 4 x 4 warps of 32 x 32)
+constexpr int TD_KC = 32;         // K chunk staged per pass
 constexpr int TD_TS = TD_TILE + 8;  // staging stride (== 8 mod 16: conflict-free fragment loads)
 constexpr int TD_PART = 2 + 2 * TD_MAXNB + TD_BC;
 
@@ -39,12 +41,14 @@ struct TridiagArgs {
   double* tau;    // T x n     tau[c+1] for column c = -1..n-2
   double* v0;     // T x n     first reflector (column -1)
   double* u;      // T x n     scratch: updated column
+  double* rsum;   // T x n     scratch: row part of the symv (owner rows)
   double* Vp;     // T x nb x n
-  double* Wp;     // T x nb x n   final W
-  double* Wraw;   // T x nb x n   W before the alpha correction
+  double* Wp;     // T x nb x n
   double* part;   // T x G x TD_PART
+  double* colpart;  // T x G x n  column part of the symv, per CTA
   double* pgram;  // T x n x nb   pgram[(c+1)*nb + t] = v_c . v_t for t < k (same panel)
   unsigned* bar;  // T
+  unsigned long long* timing;  // optional (debug): 8 accumulated phase times in ns, CTA 0 of matrix 0
   int n, G, nb, LR, nv;
 };
 
@@ -56,32 +60,39 @@ struct GroupBarrier {
     __syncthreads();
     if (threadIdx.x == 0) {
       epoch += 1;
-      __threadfence();
-      atomicAdd(ctr, 1u);
+      // release-arrive / acquire-poll on a monotonically increasing counter (no reset needed)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
       const unsigned target = epoch * G;
       unsigned long long spins = 0;
       while (true) {
         unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr));
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if (v >= target) break;
         if (++spins > (1ull << 34)) { asm volatile("trap;"); }
       }
-      __threadfence();
     }
     __syncthreads();
   }
 };
 
-__device__ __forceinline__ int owner_of(int i, int G) { return (i / TD_RB) % G; }
+// Row chunks of TD_RB rows are dealt to the G CTAs in zigzag order (0..G-1, G-1..0, ...) so that the
+// triangular row lengths balance across CTAs.
+__device__ __forceinline__ int chunk_row0(int ch, int g, int G) {
+  const int gg = (ch & 1) ? (G - 1 - g) : g;
+  return (ch * G + gg) * TD_RB;
+}
 __device__ __forceinline__ int global_row(int lr, int g, int G) {
-  return ((lr / TD_RB) * G + g) * TD_RB + (lr % TD_RB);
+  return chunk_row0(lr / TD_RB, g, G) + (lr % TD_RB);
 }
 
+// Lower-triangle storage: only A[i][j], j <= i, of the trailing block is kept up to date; the strictly upper
+// part of row c receives the reflector of column c.
 __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int n = a.n, G = a.G, nb = a.nb, LR = a.LR, ldk = a.ldk;
+  const int n = a.n, G = a.G, nb = a.nb, LR = a.LR, ldk = a.ldk, nv = a.nv;
   const int g = blockIdx.x, m = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = TD_THREADS / 32;
 
   double* A = a.K + (size_t)m * a.strideK;
   const double* ga = a.ga + (size_t)m * n;
@@ -92,227 +103,317 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
   double* tauv = a.tau + (size_t)m * n;
   double* v0 = a.v0 + (size_t)m * n;
   double* ug = a.u + (size_t)m * n;
+  double* rsum = a.rsum + (size_t)m * n;
   double* Vp = a.Vp + (size_t)m * nb * n;
   double* Wp = a.Wp + (size_t)m * nb * n;
-  double* Wraw = a.Wraw + (size_t)m * nb * n;
   double* part = a.part + (size_t)m * G * TD_PART;
   double* mypart = part + (size_t)g * TD_PART;
+  double* colpart = a.colpart + (size_t)m * G * n;
+  double* mycol = colpart + (size_t)g * n;
   double* pgram = a.pgram + (size_t)m * n * nb;
 
-  // ---- shared memory carve-up
-  const int stage_doubles = 2 * (2 * TD_MAXNB) * TD_TS;
-  const int r0_doubles = max(a.nv + 2 * LR, stage_doubles);
-  double* v = smem;                 // nv (aliased by the syr2k staging)
-  double* ys = v + a.nv;            // LR
-  double* vloc = ys + LR;           // LR
-  double* Pa = smem;                // staging alias
-  double* Pb = smem + (2 * TD_MAXNB) * TD_TS;
-  double* Vs = smem + r0_doubles;   // nb x LR
+  // ---- shared memory carve-up (region 0 is aliased by the syr2k operand staging)
+  const int stage_doubles = 2 * TD_KC * TD_TS;
+  const int r0_doubles = max(2 * nv + 2 * LR, stage_doubles);
+  double* v = smem;                   // nv, zero outside [R0, n)
+  double* ycol = v + nv;              // nv
+  double* ys = ycol + nv;             // LR
+  double* vloc = ys + LR;             // LR
+  double* Pa = smem;
+  double* Pb = smem + TD_KC * TD_TS;
+  double* rowpart = smem + r0_doubles;       // NW x LR
+  double* Vs = rowpart + (size_t)NW * LR;    // nb x LR
   double* Ws = Vs + (size_t)nb * LR;
-  double* cV = Ws + (size_t)nb * LR;  // 32
+  double* cV = Ws + (size_t)nb * LR;         // 32 each
   double* cW = cV + TD_MAXNB;
   double* Vc = cW + TD_MAXNB;
   double* Wc = Vc + TD_MAXNB;
-  double* cB = Wc + TD_MAXNB;       // 128
-  double* Bred = cB + TD_BC;        // 4 x 128
-  double* red = Bred + 4 * TD_BC;   // 40
-  double* sc = red + 40;            // scalars: [0]=alpha_prev [1]=tau [2]=beta [3]=scale
+  double* cB = Wc + TD_MAXNB;                // 128
+  double* Bred = cB + TD_BC;                 // 4 x 128
+  double* red = Bred + 4 * TD_BC;            // 40
+  double* sc = red + 40;                     // [0]=alpha [1]=tau [2]=beta [3]=scale [4]=vAv
 
   GroupBarrier bar{a.bar + m, (unsigned)G, 0u};
 
-  for (int i = tid; i < a.nv; i += TD_THREADS) v[i] = 0.0;
-  for (int i = tid; i < 2 * nb * LR; i += TD_THREADS) Vs[i] = 0.0;
+  for (int i = tid; i < r0_doubles; i += TD_THREADS) smem[i] = 0.0;
+  for (int i = tid; i < NW * LR + 2 * nb * LR; i += TD_THREADS) rowpart[i] = 0.0;
   __syncthreads();
 
-  int jj0 = -1;          // first column of the current panel
-  double tau_prev = 0.0;
+  // ---- prologue: "column -1" is ga
+  {
+    double ss = 0.0;
+    for (int lr = tid; lr < LR; lr += TD_THREADS) {
+      const int i = global_row(lr, g, G);
+      if (i < n) {
+        const double x = ga[i];
+        ug[i] = x;
+        if (i > 0) ss += x * x;
+      }
+    }
+    ss = block_sum(ss, red);
+    if (tid == 0) mypart[0] = ss;
+  }
+  bar.sync();
+
+  int jj0 = -1;  // first column of the current panel
+  const bool timed = a.timing && g == 0 && m == 0 && tid == 0;
+  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = 0;
+#define TD_TICK(slot)                                              \
+  if (timed) {                                                     \
+    unsigned long long now_;                                       \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));      \
+    tacc[slot] += now_ - tprev;                                    \
+    tprev = now_;                                                  \
+  }
+  if (timed) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tprev));
 
   for (int c = -1; c <= n - 2; ++c) {
-    const int k = c - jj0;   // panel vectors already built
+    const int k = c - jj0;  // panel vectors already built
     const int R0 = c + 1;
 
-    // ================= phase A: finish W_{k-1}, update column c, partial norm
-    if (k > 0) {
+    // ================= phase B: reflector, symv (lower triangle), partial products
+    if (wid == 0) {
       double s = 0.0;
-      if (wid == 0) {
-        for (int q = lane; q < G; q += 32) s += ldcg(part + (size_t)q * TD_PART + 1);
-        s = warp_sum(s);
-        if (lane == 0) sc[0] = -0.5 * tau_prev * s;
-      }
-      __syncthreads();
-      const double alpha = sc[0];
-      for (int lr = tid; lr < LR; lr += TD_THREADS) {
-        const int i = global_row(lr, g, G);
-        const double wf = Ws[(k - 1) * LR + lr] + alpha * Vs[(k - 1) * LR + lr];
-        Ws[(k - 1) * LR + lr] = wf;
-        if (i < n) Wp[(size_t)(k - 1) * n + i] = wf;
-      }
-      if (tid < k) {
-        Vc[tid] = ldcg(Vp + (size_t)tid * n + c);
-        Wc[tid] = (tid < k - 1) ? ldcg(Wp + (size_t)tid * n + c)
-                                : ldcg(Wraw + (size_t)tid * n + c) + alpha * ldcg(Vp + (size_t)tid * n + c);
+      for (int q = lane; q < G; q += 32) s += ldcg(part + (size_t)q * TD_PART + 0);
+      s = warp_sum(s);
+      if (lane == 0) {
+        const double alpha0 = ldcg(ug + R0);
+        double beta, tau, scale;
+        if (s == 0.0) {
+          beta = alpha0; tau = 0.0; scale = 0.0;
+        } else {
+          beta = -copysign(sqrt(alpha0 * alpha0 + s), alpha0);
+          tau = (beta - alpha0) / beta;
+          scale = 1.0 / (alpha0 - beta);
+        }
+        sc[1] = tau; sc[2] = beta; sc[3] = scale;
       }
     }
     __syncthreads();
+    const double tau = sc[1];
     {
-      double ss = 0.0;
-      for (int lr = tid; lr < LR; lr += TD_THREADS) {
-        const int i = global_row(lr, g, G);
-        if (i >= R0 && i < n) {
-          double x;
-          if (c < 0) {
-            x = ga[i];
-          } else {
-            x = ldcg(A + (size_t)c * ldk + i);
-            for (int t = 0; t < k; ++t) x -= Vs[t * LR + lr] * Wc[t] + Ws[t * LR + lr] * Vc[t];
-          }
-          ug[i] = x;
-          if (i > R0) ss += x * x;
-        }
-      }
-      ss = block_sum(ss, red);
-      if (tid == 0) {
-        mypart[0] = ss;
-        if (g == 0 && c >= 0) {
-          double x = ldcg(A + (size_t)c * ldk + c);
-          for (int t = 0; t < k; ++t) x -= 2.0 * Vc[t] * Wc[t];
-          dd[c] = x;
-        }
-      }
-    }
-    bar.sync();
-
-    // ================= phase B: reflector, symv, panel/B partial products
-    {
-      if (wid == 0) {
-        double s = 0.0;
-        for (int q = lane; q < G; q += 32) s += ldcg(part + (size_t)q * TD_PART + 0);
-        s = warp_sum(s);
-        if (lane == 0) {
-          const double alpha0 = ldcg(ug + R0);
-          double beta, tau, scale;
-          if (s == 0.0) {
-            beta = alpha0; tau = 0.0; scale = 0.0;
-          } else {
-            beta = -copysign(sqrt(alpha0 * alpha0 + s), alpha0);
-            tau = (beta - alpha0) / beta;
-            scale = 1.0 / (alpha0 - beta);
-          }
-          sc[1] = tau; sc[2] = beta; sc[3] = scale;
-        }
-      }
-      __syncthreads();
-      const double tau = sc[1], scale = sc[3];
+      const double scale = sc[3];
       if (g == 0 && tid == 0) {
         if (c < 0) a.beta0[m] = sc[2]; else ee[c] = sc[2];
         tauv[c + 1] = tau;
       }
-      for (int i = R0 + tid; i < n; i += TD_THREADS) v[i] = (i == R0) ? 1.0 : ldcg(ug + i) * scale;
+      for (int i = R0 + tid; i < n; i += TD_THREADS) {
+        v[i] = (i == R0) ? 1.0 : ldcg(ug + i) * scale;
+        ycol[i] = 0.0;
+      }
       if (tid == 0 && R0 > 0) v[R0 - 1] = 0.0;
-      __syncthreads();
-      for (int lr = tid; lr < LR; lr += TD_THREADS) {
-        const int i = global_row(lr, g, G);
-        const double x = (i >= R0 && i < n) ? v[i] : 0.0;
-        vloc[lr] = x;
-        Vs[k * LR + lr] = x;
-        if (i < n) {
-          Vp[(size_t)k * n + i] = x;
-          if (i >= R0) {
-            if (c < 0) v0[i] = x; else A[(size_t)c * ldk + i] = x;
-          }
+    }
+    __syncthreads();
+    for (int lr = tid; lr < LR; lr += TD_THREADS) {
+      const int i = global_row(lr, g, G);
+      const double x = (i >= R0 && i < n) ? v[i] : 0.0;
+      vloc[lr] = x;
+      Vs[k * LR + lr] = x;
+      if (i < n) {
+        Vp[(size_t)k * n + i] = x;
+        if (i >= R0) {
+          if (c < 0) v0[i] = x; else A[(size_t)c * ldk + i] = x;
         }
-      }
-      __syncthreads();
-      // symv over the (not yet updated) trailing block: one warp per owned row
-      const int jb = R0 & ~1;
-      const int je = n & ~1;   // an odd last column is added by lane 0 (never touch the padding)
-      for (int lr = wid; lr < LR; lr += TD_THREADS / 32) {
-        const int i = global_row(lr, g, G);
-        if (i < R0 || i >= n) continue;
-        const double2* row = reinterpret_cast<const double2*>(A + (size_t)i * ldk);
-        const double2* vv = reinterpret_cast<const double2*>(v);
-        double s0 = 0.0, s1 = 0.0;
-        int j2 = (jb >> 1) + lane;
-        const int e2 = je >> 1;
-        for (; j2 + 96 < e2; j2 += 128) {
-          double2 x0 = ldcg2(row + j2), x1 = ldcg2(row + j2 + 32), x2 = ldcg2(row + j2 + 64),
-                  x3 = ldcg2(row + j2 + 96);
-          double2 y0 = vv[j2], y1 = vv[j2 + 32], y2 = vv[j2 + 64], y3 = vv[j2 + 96];
-          s0 += x0.x * y0.x; s1 += x0.y * y0.y;
-          s0 += x1.x * y1.x; s1 += x1.y * y1.y;
-          s0 += x2.x * y2.x; s1 += x2.y * y2.y;
-          s0 += x3.x * y3.x; s1 += x3.y * y3.y;
-        }
-        for (; j2 < e2; j2 += 32) {
-          double2 x0 = ldcg2(row + j2);
-          double2 y0 = vv[j2];
-          s0 += x0.x * y0.x; s1 += x0.y * y0.y;
-        }
-        if ((n & 1) && lane == 0) s0 += ldcg(A + (size_t)i * ldk + (n - 1)) * v[n - 1];
-        const double s = warp_sum(s0 + s1);
-        if (lane == 0) ys[lr] = s;
-      }
-      // panel partial products  pV_t = V_t . v,  pW_t = W_t . v   (t < k)
-      for (int task = wid; task < 2 * k; task += TD_THREADS / 32) {
-        const double* src = (task < k) ? (Vs + (size_t)task * LR) : (Ws + (size_t)(task - k) * LR);
-        double s = 0.0;
-        for (int lr = lane; lr < LR; lr += 32) s += src[lr] * vloc[lr];
-        s = warp_sum(s);
-        if (lane == 0) mypart[2 + task] = s;
-      }
-      // B^T v partial
-      if (nbc > 0) {
-        const int col = tid & (TD_BC - 1), grp = tid >> 7;
-        double s = 0.0;
-        if (col < nbc) {
-          for (int lr = grp; lr < LR; lr += 4) {
-            const double x = vloc[lr];
-            if (x != 0.0) {
-              const int i = global_row(lr, g, G);
-              s += ldcg(Bm + (size_t)i * ldb + col) * x;
-            }
-          }
-        }
-        Bred[grp * TD_BC + col] = s;
-        __syncthreads();
-        if (tid < nbc)
-          mypart[2 + 2 * TD_MAXNB + tid] = Bred[tid] + Bred[TD_BC + tid] + Bred[2 * TD_BC + tid] + Bred[3 * TD_BC + tid];
       }
     }
-    bar.sync();
-
-    // ================= phase C: w' = tau (y - V (W^T v) - W (V^T v)), B update
+    TD_TICK(0)
+    // ---- symv on the stored lower triangle: 16 rows x 32 columns per warp iteration
     {
-      const double tau = sc[1];
-      const int nval = 2 * k + nbc;
-      for (int q = wid; q < nval; q += TD_THREADS / 32) {
-        const int slot = (q < 2 * k) ? (2 + q) : (2 + 2 * TD_MAXNB + (q - 2 * k));
-        double s = 0.0;
-        for (int h = lane; h < G; h += 32) s += ldcg(part + (size_t)h * TD_PART + slot);
-        s = warp_sum(s);
-        if (lane == 0) {
-          if (q < k) cV[q] = s;
-          else if (q < 2 * k) cW[q - k] = s;
-          else cB[q - 2 * k] = s;
+      const int jbase = R0 & ~31;
+      for (int ch = 0; ch < LR / TD_RB; ++ch) {
+        const int i0 = chunk_row0(ch, g, G);
+        if (i0 + TD_RB - 1 < R0 || i0 >= n) continue;
+        double racc[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) racc[r] = 0.0;
+        const int jmax = min(i0 + TD_RB - 1, n - 1);
+        const int nstrips = (jmax - jbase) / 32 + 1;
+        for (int s = wid; s < nstrips; s += NW) {
+          const int js = jbase + 32 * s;
+          const int j = js + lane;
+          double colacc = 0.0;
+          if (js >= R0 && js + 31 < i0 && i0 >= R0 && i0 + TD_RB - 1 < n) {
+            const double vj = v[j];
+            const double* p = A + (size_t)i0 * ldk + j;
+            double av[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) av[r] = ldcg(p + (size_t)r * ldk);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              racc[r] = fma(av[r], vj, racc[r]);
+              colacc = fma(av[r], v[i0 + r], colacc);
+            }
+            ycol[j] += colacc;
+          } else {
+            const bool jok = (j >= R0) && (j <= jmax);
+            const double vj = jok ? v[j] : 0.0;
+            double av[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int i = i0 + r;
+              const bool ok = jok && (i >= R0) && (i < n) && (j <= i);
+              av[r] = ok ? ldcg(A + (size_t)i * ldk + j) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int i = i0 + r;
+              racc[r] = fma(av[r], vj, racc[r]);
+              if (j < i) colacc = fma(av[r], v[i], colacc);
+            }
+            if (jok) ycol[j] += colacc;
+          }
+        }
+        // butterfly reduction of the 16 row accumulators over the warp (16 shuffles)
+        double t8[8], t4[4], t2[2], t1;
+        {
+          const bool hi = lane & 16;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const double send = hi ? racc[r] : racc[r + 8];
+            const double keep = hi ? racc[r + 8] : racc[r];
+            t8[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+        }
+        {
+          const bool hi = lane & 8;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double send = hi ? t8[r] : t8[r + 4];
+            const double keep = hi ? t8[r + 4] : t8[r];
+            t4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+        }
+        {
+          const bool hi = lane & 4;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const double send = hi ? t4[r] : t4[r + 2];
+            const double keep = hi ? t4[r + 2] : t4[r];
+            t2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool hi = lane & 2;
+          const double send = hi ? t2[0] : t2[1];
+          const double keep = hi ? t2[1] : t2[0];
+          t1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+        if ((lane & 1) == 0) {
+          const int r = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          rowpart[wid * LR + ch * TD_RB + r] = t1;
         }
       }
+    }
+    __syncthreads();
+    TD_TICK(1)
+    for (int lr = tid; lr < LR; lr += TD_THREADS) {
+      const int i = global_row(lr, g, G);
+      double s = 0.0;
+      if (i >= R0 && i < n) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += rowpart[w * LR + lr];
+        rsum[i] = s;
+      }
+      ys[lr] = s;
+    }
+    double colv = 0.0;
+    for (int j = R0 + tid; j < n; j += TD_THREADS) {
+      const double yc = ycol[j];
+      mycol[j] = yc;
+      colv = fma(v[j], yc, colv);
+    }
+    colv = block_sum(colv, red);
+    // panel partial products pV_t = V_t . v, pW_t = W_t . v (t < k) and the local share of v^T A v
+    for (int task = wid; task < 2 * k + 1; task += NW) {
+      double s = 0.0;
+      if (task < 2 * k) {
+        const double* src = (task < k) ? (Vs + (size_t)task * LR) : (Ws + (size_t)(task - k) * LR);
+        for (int lr = lane; lr < LR; lr += 32) s += src[lr] * vloc[lr];
+      } else {
+        for (int lr = lane; lr < LR; lr += 32) s += ys[lr] * vloc[lr];
+      }
+      s = warp_sum(s);
+      if (lane == 0) mypart[(task < 2 * k) ? (2 + task) : 1] = (task < 2 * k) ? s : s + colv;
+    }
+    if (nbc > 0) {
+      const int col = tid & (TD_BC - 1), grp = tid >> 7;
+      double s = 0.0;
+      if (col < nbc) {
+        for (int lr = grp; lr < LR; lr += 4) {
+          const double x = vloc[lr];
+          if (x != 0.0) {
+            const int i = global_row(lr, g, G);
+            s += ldcg(Bm + (size_t)i * ldb + col) * x;
+          }
+        }
+      }
+      Bred[grp * TD_BC + col] = s;
       __syncthreads();
+      if (tid < nbc)
+        mypart[2 + 2 * TD_MAXNB + tid] = Bred[tid] + Bred[TD_BC + tid] + Bred[2 * TD_BC + tid] + Bred[3 * TD_BC + tid];
+    }
+    TD_TICK(2)
+    bar.sync();
+    TD_TICK(3)
+
+    // ================= phase C: w = tau (A v - V (W^T v) - W (V^T v)) + alpha v, B update
+    {
+      const int nval = 2 * k + nbc + 1;   // <= 193
+      {
+        // every value is the sum of G per-CTA partials: 2 threads per value, independent loads
+        const int q = tid & 255, h0 = tid >> 8;
+        double s = 0.0;
+        if (q < nval) {
+          int slot;
+          if (q < 2 * k) slot = 2 + q;
+          else if (q < 2 * k + nbc) slot = 2 + 2 * TD_MAXNB + (q - 2 * k);
+          else slot = 1;
+          for (int h = h0; h < G; h += 2) s += ldcg(part + (size_t)h * TD_PART + slot);
+        }
+        Bred[h0 * 256 + q] = s;
+      }
+      if (tid < k) {   // panel vectors at the pivot row of the next column (final since >= 1 barrier)
+        Vc[tid] = ldcg(Vp + (size_t)tid * n + R0);
+        Wc[tid] = ldcg(Wp + (size_t)tid * n + R0);
+      }
+      // column part of y for the owned rows: 4 threads per row
+      for (int idx = tid; idx < 4 * LR; idx += TD_THREADS) {
+        const int lr = idx % LR, p4 = idx / LR;
+        const int i = global_row(lr, g, G);
+        double y = 0.0;
+        if (i >= R0 && i < n)
+          for (int q = p4; q < G; q += 4) y += ldcg(colpart + (size_t)q * n + i);
+        rowpart[p4 * LR + lr] = y;
+      }
+      __syncthreads();
+      if (tid < nval) {
+        const double s = Bred[tid] + Bred[256 + tid];
+        if (tid < k) cV[tid] = s;
+        else if (tid < 2 * k) cW[tid - k] = s;
+        else if (tid < 2 * k + nbc) cB[tid - 2 * k] = s;
+        else sc[4] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double cc = 0.0;
+        for (int t = 0; t < k; ++t) cc += cV[t] * cW[t];
+        sc[0] = -0.5 * tau * tau * (sc[4] - 2.0 * cc);
+      }
       if (g == 0 && tid < k) pgram[(size_t)(c + 1) * nb + tid] = cV[tid];
-      double dot = 0.0;
+      __syncthreads();
+      const double alpha = sc[0];
       for (int lr = tid; lr < LR; lr += TD_THREADS) {
         const int i = global_row(lr, g, G);
         double wv = 0.0;
         if (i >= R0 && i < n) {
-          double y = ys[lr];
+          double y = ys[lr] + ((rowpart[lr] + rowpart[LR + lr]) + (rowpart[2 * LR + lr] + rowpart[3 * LR + lr]));
           for (int t = 0; t < k; ++t) y -= Vs[t * LR + lr] * cW[t] + Ws[t * LR + lr] * cV[t];
-          wv = tau * y;
-          dot += wv * vloc[lr];
+          wv = tau * y + alpha * vloc[lr];
         }
         Ws[k * LR + lr] = wv;
-        if (i < n) Wraw[(size_t)k * n + i] = wv;
+        if (i < n) Wp[(size_t)k * n + i] = wv;
       }
-      dot = block_sum(dot, red);
-      if (tid == 0) mypart[1] = dot;
       if (nbc > 0 && tau != 0.0) {
         const int col = tid & (TD_BC - 1), grp = tid >> 7;
         if (col < nbc) {
@@ -327,94 +428,137 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
           }
         }
       }
-      tau_prev = tau;
-    }
-    bar.sync();
-
-    // ================= panel end: trailing update on the FP64 tensor cores
-    if (k + 1 == nb || c == n - 2) {
-      const int kp = k + 1;
-      {  // finish W_{kp-1}
-        if (wid == 0) {
+      const bool panel_end = (k + 1 == nb) || (c == n - 2);
+      if (!panel_end) {
+        // W_k at the pivot row of the next column (row R0), needed by every CTA
+        if (wid == 1) {
           double s = 0.0;
-          for (int q = lane; q < G; q += 32) s += ldcg(part + (size_t)q * TD_PART + 1);
+          for (int q = lane; q < G; q += 32) s += ldcg(colpart + (size_t)q * n + R0);
           s = warp_sum(s);
-          if (lane == 0) sc[0] = -0.5 * tau_prev * s;
-        }
-        __syncthreads();
-        const double alpha = sc[0];
-        for (int lr = tid; lr < LR; lr += TD_THREADS) {
-          const int i = global_row(lr, g, G);
-          const double wf = Ws[(kp - 1) * LR + lr] + alpha * Vs[(kp - 1) * LR + lr];
-          if (i < n) Wp[(size_t)(kp - 1) * n + i] = wf;
-        }
-      }
-      bar.sync();
-      const int Rn = c + 1;   // trailing block is rows/cols > c
-      const int t0 = Rn / TD_TILE, t1 = (n + TD_TILE - 1) / TD_TILE;
-      const int nt = t1 - t0;
-      const int kk_end = (2 * kp + 3) & ~3;
-      const int wm = wid >> 2, wn = wid & 3;
-      const int fr = lane >> 2, fk = lane & 3;
-      for (int tile = g; tile < nt * nt; tile += G) {
-        const int ti = t0 + tile / nt, tj = t0 + tile % nt;
-        const int i0 = ti * TD_TILE, j0 = tj * TD_TILE;
-        __syncthreads();
-        for (int q = tid; q < kk_end * TD_TILE; q += TD_THREADS) {
-          const int kk = q / TD_TILE, r = q % TD_TILE;
-          double pa = 0.0, pb = 0.0;
-          if (kk < 2 * kp) {
-            const double* srcA = (kk < kp) ? (Vp + (size_t)kk * n) : (Wp + (size_t)(kk - kp) * n);
-            const double* srcB = (kk < kp) ? (Wp + (size_t)kk * n) : (Vp + (size_t)(kk - kp) * n);
-            if (i0 + r < n) pa = ldcg(srcA + i0 + r);
-            if (j0 + r < n) pb = ldcg(srcB + j0 + r);
-          }
-          Pa[kk * TD_TS + r] = pa;
-          Pb[kk * TD_TS + r] = pb;
-        }
-        __syncthreads();
-        double acc[2][2][2] = {};
-        for (int kk = 0; kk < kk_end; kk += 4) {
-          double af[2], bf[2];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            af[x] = Pa[(kk + fk) * TD_TS + wm * 16 + x * 8 + fr];
-            bf[x] = Pb[(kk + fk) * TD_TS + wn * 16 + x * 8 + fr];
-          }
-#pragma unroll
-          for (int x = 0; x < 2; ++x)
-#pragma unroll
-            for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-        }
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          const int i = i0 + wm * 16 + x * 8 + fr;
-#pragma unroll
-          for (int y = 0; y < 2; ++y) {
-            const int j = j0 + wn * 16 + y * 8 + 2 * fk;
-            if (i >= Rn && i < n) {
-              double* p = A + (size_t)i * ldk + j;
-              if (j >= Rn && j + 1 < n) {
-                double2 o = ldcg2(reinterpret_cast<const double2*>(p));
-                o.x -= acc[x][y][0];
-                o.y -= acc[x][y][1];
-                *reinterpret_cast<double2*>(p) = o;
-              } else {
-                if (j >= Rn && j < n) p[0] = ldcg(p) - acc[x][y][0];
-                if (j + 1 >= Rn && j + 1 < n) p[1] = ldcg(p + 1) - acc[x][y][1];
-              }
-            }
+          if (lane == 0) {
+            double y = s + ldcg(rsum + R0);
+            for (int t = 0; t < k; ++t) y -= Vc[t] * cW[t] + Wc[t] * cV[t];
+            Wc[k] = tau * y + alpha;   // v[R0] == 1
+            Vc[k] = 1.0;
           }
         }
       }
       __syncthreads();
-      // staging aliased v/ys/vloc: restore the invariant v[i < R0_next] == 0 (rest is rewritten)
-      for (int i = tid; i < a.nv; i += TD_THREADS) v[i] = 0.0;
-      for (int i = tid; i < 2 * nb * LR; i += TD_THREADS) Vs[i] = 0.0;
-      bar.sync();
-      jj0 = c + 1;
+      TD_TICK(4)
+
+      // ================= panel end: rank-2kp update of the lower triangle on the FP64 tensor cores
+      if (panel_end) {
+        const int kp = k + 1;
+        bar.sync();
+        const int Rn = c + 1;  // trailing block is rows/cols > c
+        const int t0 = Rn / TD_TILE, t1 = (n + TD_TILE - 1) / TD_TILE;
+        const int nt = t1 - t0;
+        const int ntiles = nt * (nt + 1) / 2;
+        const int kk_end = (2 * kp + 3) & ~3;
+        const int wm = wid >> 2, wn = wid & 3;   // 4 x 4 warps, warp tile 32 x 32
+        const int fr = lane >> 2, fk = lane & 3;
+        for (int tile = g; tile < ntiles; tile += G) {
+          int bi = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+          while ((bi + 1) * (bi + 2) / 2 <= tile) ++bi;
+          while (bi * (bi + 1) / 2 > tile) --bi;
+          const int bj = tile - bi * (bi + 1) / 2;
+          const int i0 = (t0 + bi) * TD_TILE, j0 = (t0 + bj) * TD_TILE;
+          double acc[4][4][2];
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+          for (int kc = 0; kc < kk_end; kc += TD_KC) {
+            const int kn_ = min(TD_KC, kk_end - kc);
+            __syncthreads();
+            for (int q = tid; q < kn_ * TD_TILE; q += TD_THREADS) {
+              const int kl = q / TD_TILE, r = q % TD_TILE, kk = kc + kl;
+              double pa = 0.0, pb = 0.0;
+              if (kk < 2 * kp) {
+                const double* srcA = (kk < kp) ? (Vp + (size_t)kk * n) : (Wp + (size_t)(kk - kp) * n);
+                const double* srcB = (kk < kp) ? (Wp + (size_t)kk * n) : (Vp + (size_t)(kk - kp) * n);
+                if (i0 + r < n) pa = ldcg(srcA + i0 + r);
+                if (j0 + r < n) pb = ldcg(srcB + j0 + r);
+              }
+              Pa[kl * TD_TS + r] = pa;
+              Pb[kl * TD_TS + r] = pb;
+            }
+            __syncthreads();
+            for (int kl = 0; kl < kn_; kl += 4) {
+              double af[4], bf[4];
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                af[x] = Pa[(kl + fk) * TD_TS + wm * 32 + x * 8 + fr];
+                bf[x] = Pb[(kl + fk) * TD_TS + wn * 32 + x * 8 + fr];
+              }
+#pragma unroll
+              for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int i = i0 + wm * 32 + x * 8 + fr;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+              const int j = j0 + wn * 32 + y * 8 + 2 * fk;
+              if (i >= Rn && i < n) {
+                double* p = A + (size_t)i * ldk + j;
+                if (j >= Rn && j + 1 <= i) {
+                  double2 o = ldcg2(reinterpret_cast<const double2*>(p));
+                  o.x -= acc[x][y][0];
+                  o.y -= acc[x][y][1];
+                  *reinterpret_cast<double2*>(p) = o;
+                } else {
+                  if (j >= Rn && j <= i) p[0] = ldcg(p) - acc[x][y][0];
+                  if (j + 1 >= Rn && j + 1 <= i) p[1] = ldcg(p + 1) - acc[x][y][1];
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        // the staging aliased v / ycol / ys / vloc: restore the all-zero state; drop the finished panel
+        for (int i = tid; i < r0_doubles; i += TD_THREADS) smem[i] = 0.0;
+        for (int i = tid; i < 2 * nb * LR; i += TD_THREADS) Vs[i] = 0.0;
+        bar.sync();
+        jj0 = c + 1;
+      }
+
+      TD_TICK(5)
+      // ================= phase A for the next column cn = c + 1
+      const int cn = c + 1;
+      if (cn <= n - 2) {
+        const int kn = cn - jj0;
+        const int R1 = cn + 1;
+        double ss = 0.0;
+        for (int lr = tid; lr < LR; lr += TD_THREADS) {
+          const int i = global_row(lr, g, G);
+          if (i >= R1 && i < n) {
+            double x = ldcg(A + (size_t)i * ldk + cn);
+            for (int t = 0; t < kn; ++t) x -= Vs[t * LR + lr] * Wc[t] + Ws[t * LR + lr] * Vc[t];
+            ug[i] = x;
+            if (i > R1) ss += x * x;
+          }
+        }
+        ss = block_sum(ss, red);
+        if (tid == 0) {
+          mypart[0] = ss;
+          if (g == 0) {
+            double x = ldcg(A + (size_t)cn * ldk + cn);
+            for (int t = 0; t < kn; ++t) x -= 2.0 * Vc[t] * Wc[t];
+            dd[cn] = x;
+          }
+        }
+        TD_TICK(6)
+        bar.sync();
+        TD_TICK(7)
+      }
     }
   }
+  if (timed)
+    for (int q = 0; q < 8; ++q) a.timing[q] = tacc[q];
   if (g == 0 && tid == 0) {
     dd[n - 1] = ldcg(A + (size_t)(n - 1) * ldk + (n - 1));
     ee[n - 1] = 0.0;
@@ -520,18 +664,20 @@ int profile_read(double* total_ms, int* launches) {
 size_t tridiag_smem_bytes(const Plan* pl) {
   const int chunks = (pl->n + TD_RB - 1) / TD_RB;
   const int LR = (chunks + pl->G - 1) / pl->G * TD_RB;
-  const int nv = (int)align_up(pl->n + 2, 2);
-  const int stage = 2 * (2 * TD_MAXNB) * TD_TS;
-  const int r0 = max(nv + 2 * LR, stage);
-  size_t doubles = (size_t)r0 + 2 * (size_t)pl->nb * LR + 4 * TD_MAXNB + TD_BC + 4 * TD_BC + 40 + 8;
+  const int nv = (int)align_up(pl->n + 34, 2);
+  const int stage = 2 * TD_KC * TD_TS;
+  const int r0 = max(2 * nv + 2 * LR, stage);
+  size_t doubles = (size_t)r0 + (size_t)(TD_THREADS / 32) * LR + 2 * (size_t)pl->nb * LR + 4 * TD_MAXNB + TD_BC +
+                   4 * TD_BC + 40 + 8;
   return doubles * sizeof(double);
 }
 
 size_t tridiag_workspace(const Plan* pl, int T) {
   const size_t n = pl->n, nb = pl->nb;
   size_t b = 0;
-  b += 3 * align_up(T * n * sizeof(double), 256);             // tau, v0, u
-  b += 3 * align_up(T * nb * n * sizeof(double), 256);        // Vp, Wp, Wraw
+  b += 4 * align_up(T * n * sizeof(double), 256);             // tau, v0, u, rsum
+  b += 2 * align_up(T * nb * n * sizeof(double), 256);        // Vp, Wp
+  b += align_up((size_t)T * pl->G * n * sizeof(double), 256); // colpart
   b += align_up((size_t)T * pl->G * TD_PART * sizeof(double), 256);
   b += align_up(T * n * nb * sizeof(double), 256);            // pgram
   b += align_up(T * sizeof(unsigned), 256);
@@ -543,9 +689,10 @@ bool tridiag_carve(const Plan* pl, int T, Carver& cv, TridiagBuffers& tb) {
   tb.tau = cv.take<double>(T * n);
   tb.v0 = cv.take<double>(T * n);
   tb.u = cv.take<double>(T * n);
+  tb.rsum = cv.take<double>(T * n);
   tb.Vp = cv.take<double>(T * nb * n);
   tb.Wp = cv.take<double>(T * nb * n);
-  tb.Wraw = cv.take<double>(T * nb * n);
+  tb.colpart = cv.take<double>((size_t)T * pl->G * n);
   tb.part = cv.take<double>((size_t)T * pl->G * TD_PART);
   tb.pgram = cv.take<double>(T * n * nb);
   tb.bar = cv.take<unsigned>(T);
@@ -560,11 +707,15 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
   TridiagArgs a;
   a.K = K; a.strideK = (size_t)n * ldk; a.ldk = ldk; a.ga = ga; a.B = B; a.ldb = ldb; a.nbc = nbc;
   a.d = d; a.e = e; a.beta0 = beta0; a.tau = tb.tau; a.v0 = tb.v0; a.u = tb.u; a.Vp = tb.Vp; a.Wp = tb.Wp;
-  a.Wraw = tb.Wraw; a.part = tb.part; a.pgram = tb.pgram; a.bar = tb.bar;
+  a.rsum = tb.rsum; a.colpart = tb.colpart; a.part = tb.part; a.pgram = tb.pgram; a.bar = tb.bar;
   a.n = n; a.G = pl->G; a.nb = pl->nb;
   a.LR = (chunks + pl->G - 1) / pl->G * TD_RB;
-  a.nv = (int)align_up(n + 2, 2);
+  a.nv = (int)align_up(n + 34, 2);
   const size_t smem = tridiag_smem_bytes(pl);
+  static unsigned long long* dbg = nullptr;
+  static const bool dbg_on = getenv("CHD_TD_TIMING") != nullptr;
+  if (dbg_on && !dbg) CHD_CUDA(cudaMalloc(&dbg, 8 * sizeof(unsigned long long)));
+  a.timing = dbg_on ? dbg : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     CHD_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
@@ -584,7 +735,8 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
     b.d = d + (size_t)t0 * n; b.e = e + (size_t)t0 * n; b.beta0 = beta0 + t0;
     b.tau = tb.tau + (size_t)t0 * n; b.v0 = tb.v0 + (size_t)t0 * n; b.u = tb.u + (size_t)t0 * n;
     b.Vp = tb.Vp + (size_t)t0 * pl->nb * n; b.Wp = tb.Wp + (size_t)t0 * pl->nb * n;
-    b.Wraw = tb.Wraw + (size_t)t0 * pl->nb * n;
+    b.rsum = tb.rsum + (size_t)t0 * n;
+    b.colpart = tb.colpart + (size_t)t0 * pl->G * n;
     b.part = tb.part + (size_t)t0 * pl->G * TD_PART;
     b.pgram = tb.pgram + (size_t)t0 * n * pl->nb;
     b.bar = tb.bar + t0;
@@ -604,6 +756,15 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
       CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].second, st));
       ++g_prof_used;
     }
+  }
+  if (dbg_on) {
+    unsigned long long h[8];
+    CHD_CUDA(cudaStreamSynchronize(st));
+    CHD_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    const char* nm[8] = {"setup", "symv", "partials", "sync2", "phaseC", "syr2k", "phaseA", "sync1"};
+    fprintf(stderr, "[tridiag timing, last wave, ms]");
+    for (int q = 0; q < 8; ++q) fprintf(stderr, " %s=%.2f", nm[q], h[q] * 1e-6);
+    fprintf(stderr, "\n");
   }
   return CHD_OK;
 }
