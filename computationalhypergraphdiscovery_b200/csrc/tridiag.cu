@@ -340,11 +340,18 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
       const int col = tid & (TD_BC - 1), grp = tid >> 7;
       double s = 0.0;
       if (col < nbc) {
-        for (int lr = grp; lr < LR; lr += 4) {
-          const double x = vloc[lr];
-          if (x != 0.0) {
-            const int i = global_row(lr, g, G);
-            s += ldcg(Bm + (size_t)i * ldb + col) * x;
+        for (int lr0 = grp; lr0 < LR; lr0 += 32) {
+          double bv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int lr = lr0 + 4 * u;
+            const bool ok = lr < LR && vloc[lr < LR ? lr : 0] != 0.0;
+            bv[u] = ok ? ldcg(Bm + (size_t)global_row(lr, g, G) * ldb + col) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int lr = lr0 + 4 * u;
+            if (lr < LR) s = fma(bv[u], vloc[lr], s);
           }
         }
       }
@@ -418,13 +425,21 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
         const int col = tid & (TD_BC - 1), grp = tid >> 7;
         if (col < nbc) {
           const double cb = tau * cB[col];
-          for (int lr = grp; lr < LR; lr += 4) {
-            const double x = vloc[lr];
-            if (x != 0.0) {
-              const int i = global_row(lr, g, G);
-              double* p = Bm + (size_t)i * ldb + col;
-              *p = ldcg(p) - x * cb;
+          // batches of 8 rows: all loads are issued before the first store (the loop would otherwise
+          // serialise on load -> store round trips)
+          for (int lr0 = grp; lr0 < LR; lr0 += 32) {
+            double bv[8];
+            double* pp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int lr = lr0 + 4 * u;
+              const bool ok = lr < LR && vloc[lr < LR ? lr : 0] != 0.0;
+              pp[u] = ok ? Bm + (size_t)global_row(lr, g, G) * ldb + col : nullptr;
+              bv[u] = ok ? ldcg(pp[u]) : 0.0;
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (pp[u]) *pp[u] = bv[u] - vloc[lr0 + 4 * u] * cb;
           }
         }
       }
