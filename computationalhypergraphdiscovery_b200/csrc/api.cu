@@ -1,6 +1,7 @@
 // C-ABI entry points: plan, workspace carving, the fused regression and the device-resident
 // prune chain (include/chd_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -123,25 +124,34 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
     else if (n <= 640) G = 4;
     else if (n <= 1536) G = 8;
     else if (n <= 3072) G = 18;
-    else if (n <= 8192) G = 37;
-    else G = 74;
+    else G = 37;
   }
   if (G > pl->sm_count) G = pl->sm_count;
   pl->G = G;
   // panel width 32 if the CTA's panel slice fits in shared memory, else 16, else more CTAs per matrix
-  auto fits = [&]() {
+  // Preferred: 256-thread CTAs, two per SM (of different matrices), so one streams while the other sits in a
+  // barrier.  Large n does not leave room for two CTAs' shared memory: one 512-thread CTA per SM then.
+  const size_t per_cta = (prop.sharedMemPerMultiprocessor - 2 * prop.reservedSharedMemPerBlock) / 2;
+  auto fits = [&](size_t budget) {
     pl->nb = 32;
-    if (tridiag_smem_bytes(pl) <= pl->smem_optin) return true;
+    if (tridiag_smem_bytes(pl) <= budget) return true;
     pl->nb = 16;
-    return tridiag_smem_bytes(pl) <= pl->smem_optin;
+    return tridiag_smem_bytes(pl) <= budget;
   };
-  while (!fits() && pl->G < pl->sm_count) pl->G += 1;
-  if (!fits()) {
+  const char* force = getenv("CHD_TD_THREADS");
+  pl->threads = 256;
+  bool ok = (!force || atoi(force) == 256) && fits(per_cta < pl->smem_optin ? per_cta : pl->smem_optin);
+  if (!ok) {
+    pl->threads = 512;
+    if (ctas_per_matrix <= 0 && n > 4096) pl->G = 37;
+    while (!(ok = fits(pl->smem_optin)) && pl->G < pl->sm_count) pl->G += 1;
+  }
+  if (!ok) {
     set_error("n=%d does not fit the tridiagonalisation's shared memory even with %d CTAs", n, pl->G);
     delete pl;
     return CHD_EINVAL;
   }
-  pl->wave = pl->sm_count / pl->G;
+  pl->wave = (pl->threads == 256 ? 2 : 1) * pl->sm_count / pl->G;
   if (pl->wave < 1) pl->wave = 1;
   *plan = (chd_plan*)pl;
   return CHD_OK;

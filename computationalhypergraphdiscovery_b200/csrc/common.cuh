@@ -33,6 +33,7 @@ struct Plan {
   int G;          // CTAs cooperating on one matrix in the tridiagonalisation
   int wave;       // matrices per cooperative launch (G * wave <= sm_count)
   int nb;         // panel width
+  int threads;    // threads per CTA of the tridiagonalisation (256: two CTAs per SM, 512: one)
   int rows_per_chunk;
   size_t smem_optin;
 };

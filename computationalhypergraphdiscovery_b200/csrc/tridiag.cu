@@ -19,13 +19,12 @@
 
 namespace chd {
 
-constexpr int TD_THREADS = 512;
 constexpr int TD_RB = 16;         // rows per ownership chunk (= warps per CTA)
 constexpr int TD_MAXNB = 32;      // panel width
 constexpr int TD_BC = 128;        // max columns of B
-constexpr int TD_TILE = 128;      // syr2k tile (TD_TILE x TD_TILE, 4 x 4 warps of 32 x 32)
-constexpr int TD_KC = 32;         // K chunk staged per pass
-constexpr int TD_TS = TD_TILE + 8;  // staging stride (== 8 mod 16: conflict-free fragment loads)
+constexpr int TD_TN = 128;        // syr2k tile: (THREADS / 4) rows x TD_TN cols, warps of 32 x 32
+constexpr int TD_KC = 16;         // K chunk staged per pass
+constexpr int TD_SB = TD_TN + 8;  // staging stride (== 8 mod 16: conflict-free fragment loads)
 constexpr int TD_PART = 2 + 2 * TD_MAXNB + TD_BC;
 
 struct TridiagArgs {
@@ -87,7 +86,14 @@ __device__ __forceinline__ int global_row(int lr, int g, int G) {
 
 // Lower-triangle storage: only A[i][j], j <= i, of the trailing block is kept up to date; the strictly upper
 // part of row c receives the reflector of column c.
-__global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
+// THREADS = 256: two CTAs (of different matrices) per SM, one streams while the other sits in a barrier;
+// THREADS = 512: one CTA per SM (large n, where the per-CTA shared memory does not allow two).
+template <int TD_THREADS>
+__global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(TridiagArgs a) {
+  constexpr int TD_TM = TD_THREADS / 4;          // syr2k tile rows
+  constexpr int TD_SA = TD_TM + 8;
+  constexpr int TD_NGRP = TD_THREADS / 128;      // row groups of the B-block loops
+  constexpr int TD_NH = TD_THREADS / 256;
   extern __shared__ __align__(16) double smem[];
   const int n = a.n, G = a.G, nb = a.nb, LR = a.LR, ldk = a.ldk, nv = a.nv;
   const int g = blockIdx.x, m = blockIdx.y;
@@ -112,16 +118,11 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
   double* mycol = colpart + (size_t)g * n;
   double* pgram = a.pgram + (size_t)m * n * nb;
 
-  // ---- shared memory carve-up (region 0 is aliased by the syr2k operand staging)
-  const int stage_doubles = 2 * TD_KC * TD_TS;
-  const int r0_doubles = max(2 * nv + 2 * LR, stage_doubles);
-  double* v = smem;                   // nv, zero outside [R0, n)
-  double* ycol = v + nv;              // nv
-  double* ys = ycol + nv;             // LR
-  double* vloc = ys + LR;             // LR
-  double* Pa = smem;
-  double* Pb = smem + TD_KC * TD_TS;
-  double* rowpart = smem + r0_doubles;       // NW x LR
+  // ---- shared memory carve-up.  The reflector v is never cached whole: v_j = ug[j] * scale is recomputed
+  // from the updated column in L2 where needed, which keeps the footprint small enough for two CTAs per SM.
+  double* ys = smem;                         // LR
+  double* vloc = ys + LR;                    // LR   v at the owned rows
+  double* rowpart = vloc + LR;               // NW x LR
   double* Vs = rowpart + (size_t)NW * LR;    // nb x LR
   double* Ws = Vs + (size_t)nb * LR;
   double* cV = Ws + (size_t)nb * LR;         // 32 each
@@ -129,14 +130,16 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
   double* Vc = cW + TD_MAXNB;
   double* Wc = Vc + TD_MAXNB;
   double* cB = Wc + TD_MAXNB;                // 128
-  double* Bred = cB + TD_BC;                 // 4 x 128
-  double* red = Bred + 4 * TD_BC;            // 40
+  double* Bred = cB + TD_BC;                 // 512
+  double* red = Bred + 512;                  // 40
   double* sc = red + 40;                     // [0]=alpha [1]=tau [2]=beta [3]=scale [4]=vAv
+  double* Pa = sc + 8;                       // syr2k operand staging
+  double* Pb = Pa + TD_KC * TD_SA;
+  double* ycol = mycol;                      // column part of the symv lives in this CTA's global (L2) slice
 
   GroupBarrier bar{a.bar + m, (unsigned)G, 0u};
 
-  for (int i = tid; i < r0_doubles; i += TD_THREADS) smem[i] = 0.0;
-  for (int i = tid; i < NW * LR + 2 * nb * LR; i += TD_THREADS) rowpart[i] = 0.0;
+  for (int i = tid; i < (2 + NW + 2 * nb) * LR; i += TD_THREADS) smem[i] = 0.0;
   __syncthreads();
 
   // ---- prologue: "column -1" is ga
@@ -197,16 +200,11 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
         if (c < 0) a.beta0[m] = sc[2]; else ee[c] = sc[2];
         tauv[c + 1] = tau;
       }
-      for (int i = R0 + tid; i < n; i += TD_THREADS) {
-        v[i] = (i == R0) ? 1.0 : ldcg(ug + i) * scale;
-        ycol[i] = 0.0;
-      }
-      if (tid == 0 && R0 > 0) v[R0 - 1] = 0.0;
+      for (int i = R0 + tid; i < n; i += TD_THREADS) ycol[i] = 0.0;
     }
-    __syncthreads();
     for (int lr = tid; lr < LR; lr += TD_THREADS) {
       const int i = global_row(lr, g, G);
-      const double x = (i >= R0 && i < n) ? v[i] : 0.0;
+      const double x = (i < R0 || i >= n) ? 0.0 : ((i == R0) ? 1.0 : ldcg(ug + i) * sc[3]);
       vloc[lr] = x;
       Vs[k * LR + lr] = x;
       if (i < n) {
@@ -217,9 +215,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
       }
     }
     TD_TICK(0)
+    __syncthreads();
+    double vav = 0.0;   // this lane's share of sum_j v_j * (column part of y)_j
     // ---- symv on the stored lower triangle: 16 rows x 32 columns per warp iteration
     {
       const int jbase = R0 & ~31;
+      const double scale_ = sc[3];
       for (int ch = 0; ch < LR / TD_RB; ++ch) {
         const int i0 = chunk_row0(ch, g, G);
         if (i0 + TD_RB - 1 < R0 || i0 >= n) continue;
@@ -233,20 +234,23 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
           const int j = js + lane;
           double colacc = 0.0;
           if (js >= R0 && js + 31 < i0 && i0 >= R0 && i0 + TD_RB - 1 < n) {
-            const double vj = v[j];
+            const double uj = ldcg(ug + j);
             const double* p = A + (size_t)i0 * ldk + j;
             double av[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) av[r] = ldcg(p + (size_t)r * ldk);
+            const double yold = ldcg(ycol + j);
+            const double vj = (j == R0) ? 1.0 : uj * scale_;
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
               racc[r] = fma(av[r], vj, racc[r]);
-              colacc = fma(av[r], v[i0 + r], colacc);
+              colacc = fma(av[r], vloc[ch * TD_RB + r], colacc);
             }
-            ycol[j] += colacc;
+            ycol[j] = yold + colacc;
+            vav = fma(vj, colacc, vav);
           } else {
             const bool jok = (j >= R0) && (j <= jmax);
-            const double vj = jok ? v[j] : 0.0;
+            const double vj = !jok ? 0.0 : ((j == R0) ? 1.0 : ldcg(ug + j) * scale_);
             double av[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -258,9 +262,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
             for (int r = 0; r < 16; ++r) {
               const int i = i0 + r;
               racc[r] = fma(av[r], vj, racc[r]);
-              if (j < i) colacc = fma(av[r], v[i], colacc);
+              if (j < i) colacc = fma(av[r], vloc[ch * TD_RB + r], colacc);
             }
-            if (jok) ycol[j] += colacc;
+            if (jok) {
+              ycol[j] = ldcg(ycol + j) + colacc;
+              vav = fma(vj, colacc, vav);
+            }
           }
         }
         // butterfly reduction of the 16 row accumulators over the warp (16 shuffles)
@@ -317,13 +324,7 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
       }
       ys[lr] = s;
     }
-    double colv = 0.0;
-    for (int j = R0 + tid; j < n; j += TD_THREADS) {
-      const double yc = ycol[j];
-      mycol[j] = yc;
-      colv = fma(v[j], yc, colv);
-    }
-    colv = block_sum(colv, red);
+    const double colv = block_sum(vav, red);
     // panel partial products pV_t = V_t . v, pW_t = W_t . v (t < k) and the local share of v^T A v
     for (int task = wid; task < 2 * k + 1; task += NW) {
       double s = 0.0;
@@ -340,17 +341,17 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
       const int col = tid & (TD_BC - 1), grp = tid >> 7;
       double s = 0.0;
       if (col < nbc) {
-        for (int lr0 = grp; lr0 < LR; lr0 += 32) {
+        for (int lr0 = grp; lr0 < LR; lr0 += 8 * TD_NGRP) {
           double bv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int lr = lr0 + 4 * u;
+            const int lr = lr0 + TD_NGRP * u;
             const bool ok = lr < LR && vloc[lr < LR ? lr : 0] != 0.0;
             bv[u] = ok ? ldcg(Bm + (size_t)global_row(lr, g, G) * ldb + col) : 0.0;
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int lr = lr0 + 4 * u;
+            const int lr = lr0 + TD_NGRP * u;
             if (lr < LR) s = fma(bv[u], vloc[lr], s);
           }
         }
@@ -358,7 +359,12 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
       Bred[grp * TD_BC + col] = s;
       __syncthreads();
       if (tid < nbc)
-        mypart[2 + 2 * TD_MAXNB + tid] = Bred[tid] + Bred[TD_BC + tid] + Bred[2 * TD_BC + tid] + Bred[3 * TD_BC + tid];
+      {
+        double bs = 0.0;
+#pragma unroll
+        for (int gq = 0; gq < TD_NGRP; ++gq) bs += Bred[gq * TD_BC + tid];
+        mypart[2 + 2 * TD_MAXNB + tid] = bs;
+      }
     }
     TD_TICK(2)
     bar.sync();
@@ -376,7 +382,16 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
           if (q < 2 * k) slot = 2 + q;
           else if (q < 2 * k + nbc) slot = 2 + 2 * TD_MAXNB + (q - 2 * k);
           else slot = 1;
-          for (int h = h0; h < G; h += 2) s += ldcg(part + (size_t)h * TD_PART + slot);
+          for (int hb = h0; hb < G; hb += 8 * TD_NH) {
+            double pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int h = hb + u * TD_NH;
+              pv[u] = (h < G) ? ldcg(part + (size_t)h * TD_PART + slot) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += pv[u];
+          }
         }
         Bred[h0 * 256 + q] = s;
       }
@@ -390,12 +405,22 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
         const int i = global_row(lr, g, G);
         double y = 0.0;
         if (i >= R0 && i < n)
-          for (int q = p4; q < G; q += 4) y += ldcg(colpart + (size_t)q * n + i);
+          for (int qb = p4; qb < G; qb += 32) {
+            double pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int q = qb + 4 * u;
+              pv[u] = (q < G) ? ldcg(colpart + (size_t)q * n + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y += pv[u];
+          }
         rowpart[p4 * LR + lr] = y;
       }
       __syncthreads();
       if (tid < nval) {
-        const double s = Bred[tid] + Bred[256 + tid];
+        double s = Bred[tid];
+        if (TD_NH > 1) s += Bred[256 + tid];
         if (tid < k) cV[tid] = s;
         else if (tid < 2 * k) cW[tid - k] = s;
         else if (tid < 2 * k + nbc) cB[tid - 2 * k] = s;
@@ -427,19 +452,19 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
           const double cb = tau * cB[col];
           // batches of 8 rows: all loads are issued before the first store (the loop would otherwise
           // serialise on load -> store round trips)
-          for (int lr0 = grp; lr0 < LR; lr0 += 32) {
+          for (int lr0 = grp; lr0 < LR; lr0 += 8 * TD_NGRP) {
             double bv[8];
             double* pp[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const int lr = lr0 + 4 * u;
+              const int lr = lr0 + TD_NGRP * u;
               const bool ok = lr < LR && vloc[lr < LR ? lr : 0] != 0.0;
               pp[u] = ok ? Bm + (size_t)global_row(lr, g, G) * ldb + col : nullptr;
               bv[u] = ok ? ldcg(pp[u]) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-              if (pp[u]) *pp[u] = bv[u] - vloc[lr0 + 4 * u] * cb;
+              if (pp[u]) *pp[u] = bv[u] - vloc[lr0 + TD_NGRP * u] * cb;
           }
         }
       }
@@ -466,76 +491,88 @@ __global__ void __launch_bounds__(TD_THREADS, 1) tridiag_kernel(TridiagArgs a) {
         const int kp = k + 1;
         bar.sync();
         const int Rn = c + 1;  // trailing block is rows/cols > c
-        const int t0 = Rn / TD_TILE, t1 = (n + TD_TILE - 1) / TD_TILE;
-        const int nt = t1 - t0;
-        const int ntiles = nt * (nt + 1) / 2;
+        const int rb0 = Rn / TD_TM, nrb = (n + TD_TM - 1) / TD_TM - rb0;
+        const int cb0 = Rn / TD_TN;
         const int kk_end = (2 * kp + 3) & ~3;
-        const int wm = wid >> 2, wn = wid & 3;   // 4 x 4 warps, warp tile 32 x 32
+        const int wm = wid >> 2, wn = wid & 3;   // (THREADS/128) x 4 warps, warp tile 32 x 32
         const int fr = lane >> 2, fk = lane & 3;
-        for (int tile = g; tile < ntiles; tile += G) {
-          int bi = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
-          while ((bi + 1) * (bi + 2) / 2 <= tile) ++bi;
-          while (bi * (bi + 1) / 2 > tile) --bi;
-          const int bj = tile - bi * (bi + 1) / 2;
-          const int i0 = (t0 + bi) * TD_TILE, j0 = (t0 + bj) * TD_TILE;
-          double acc[4][4][2];
+        int tile_id = 0;
+        for (int rb = 0; rb < nrb; ++rb) {
+          const int i0 = (rb0 + rb) * TD_TM;
+          const int ncb = (i0 + TD_TM - 1) / TD_TN - cb0 + 1;   // column blocks touching the lower triangle
+          for (int cb = 0; cb < ncb; ++cb, ++tile_id) {
+            if (tile_id % G != g) continue;
+            const int j0 = (cb0 + cb) * TD_TN;
+            double acc[4][4][2];
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < 4; ++x)
 #pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-          for (int kc = 0; kc < kk_end; kc += TD_KC) {
-            const int kn_ = min(TD_KC, kk_end - kc);
-            __syncthreads();
-            for (int q = tid; q < kn_ * TD_TILE; q += TD_THREADS) {
-              const int kl = q / TD_TILE, r = q % TD_TILE, kk = kc + kl;
-              double pa = 0.0, pb = 0.0;
-              if (kk < 2 * kp) {
-                const double* srcA = (kk < kp) ? (Vp + (size_t)kk * n) : (Wp + (size_t)(kk - kp) * n);
-                const double* srcB = (kk < kp) ? (Wp + (size_t)kk * n) : (Vp + (size_t)(kk - kp) * n);
-                if (i0 + r < n) pa = ldcg(srcA + i0 + r);
-                if (j0 + r < n) pb = ldcg(srcB + j0 + r);
+              for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+            for (int kc = 0; kc < kk_end; kc += TD_KC) {
+              const int kn_ = min(TD_KC, kk_end - kc);
+              __syncthreads();
+              for (int q = tid; q < kn_ * TD_TN; q += TD_THREADS) {
+                const int kl = q / TD_TN, r = q % TD_TN, kk = kc + kl;
+                double pa = 0.0, pb = 0.0;
+                if (kk < 2 * kp) {
+                  const double* srcA = (kk < kp) ? (Vp + (size_t)kk * n) : (Wp + (size_t)(kk - kp) * n);
+                  const double* srcB = (kk < kp) ? (Wp + (size_t)kk * n) : (Vp + (size_t)(kk - kp) * n);
+                  if (r < TD_TM && i0 + r < n) pa = ldcg(srcA + i0 + r);
+                  if (j0 + r < n) pb = ldcg(srcB + j0 + r);
+                }
+                if (r < TD_TM) Pa[kl * TD_SA + r] = pa;
+                Pb[kl * TD_SB + r] = pb;
               }
-              Pa[kl * TD_TS + r] = pa;
-              Pb[kl * TD_TS + r] = pb;
-            }
-            __syncthreads();
-            for (int kl = 0; kl < kn_; kl += 4) {
-              double af[4], bf[4];
+              __syncthreads();
+              for (int kl = 0; kl < kn_; kl += 4) {
+                double af[4], bf[4];
 #pragma unroll
-              for (int x = 0; x < 4; ++x) {
-                af[x] = Pa[(kl + fk) * TD_TS + wm * 32 + x * 8 + fr];
-                bf[x] = Pb[(kl + fk) * TD_TS + wn * 32 + x * 8 + fr];
+                for (int x = 0; x < 4; ++x) {
+                  af[x] = Pa[(kl + fk) * TD_SA + wm * 32 + x * 8 + fr];
+                  bf[x] = Pb[(kl + fk) * TD_SB + wn * 32 + x * 8 + fr];
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                  for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
               }
-#pragma unroll
-              for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
             }
-          }
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const int i = i0 + wm * 32 + x * 8 + fr;
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-              const int j = j0 + wn * 32 + y * 8 + 2 * fk;
+            for (int x = 0; x < 4; ++x) {
+              const int i = i0 + wm * 32 + x * 8 + fr;
               if (i >= Rn && i < n) {
-                double* p = A + (size_t)i * ldk + j;
-                if (j >= Rn && j + 1 <= i) {
-                  double2 o = ldcg2(reinterpret_cast<const double2*>(p));
-                  o.x -= acc[x][y][0];
-                  o.y -= acc[x][y][1];
-                  *reinterpret_cast<double2*>(p) = o;
-                } else {
-                  if (j >= Rn && j <= i) p[0] = ldcg(p) - acc[x][y][0];
-                  if (j + 1 >= Rn && j + 1 <= i) p[1] = ldcg(p + 1) - acc[x][y][1];
+                // all loads of the row first, then the stores (otherwise every element is a serial round trip)
+                double2 o[4];
+                bool full[4];
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                  const int j = j0 + wn * 32 + y * 8 + 2 * fk;
+                  full[y] = (j >= Rn) && (j + 1 <= i);
+                  const double* p = A + (size_t)i * ldk + j;
+                  if (full[y]) {
+                    o[y] = ldcg2(reinterpret_cast<const double2*>(p));
+                  } else {
+                    o[y].x = (j >= Rn && j <= i) ? ldcg(p) : 0.0;
+                    o[y].y = (j + 1 >= Rn && j + 1 <= i) ? ldcg(p + 1) : 0.0;
+                  }
+                }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                  const int j = j0 + wn * 32 + y * 8 + 2 * fk;
+                  double* p = A + (size_t)i * ldk + j;
+                  if (full[y]) {
+                    *reinterpret_cast<double2*>(p) = make_double2(o[y].x - acc[x][y][0], o[y].y - acc[x][y][1]);
+                  } else {
+                    if (j >= Rn && j <= i) p[0] = o[y].x - acc[x][y][0];
+                    if (j + 1 >= Rn && j + 1 <= i) p[1] = o[y].y - acc[x][y][1];
+                  }
                 }
               }
             }
           }
         }
         __syncthreads();
-        // the staging aliased v / ycol / ys / vloc: restore the all-zero state; drop the finished panel
-        for (int i = tid; i < r0_doubles; i += TD_THREADS) smem[i] = 0.0;
+        // drop the finished panel
         for (int i = tid; i < 2 * nb * LR; i += TD_THREADS) Vs[i] = 0.0;
         bar.sync();
         jj0 = c + 1;
@@ -679,11 +716,8 @@ int profile_read(double* total_ms, int* launches) {
 size_t tridiag_smem_bytes(const Plan* pl) {
   const int chunks = (pl->n + TD_RB - 1) / TD_RB;
   const int LR = (chunks + pl->G - 1) / pl->G * TD_RB;
-  const int nv = (int)align_up(pl->n + 34, 2);
-  const int stage = 2 * TD_KC * TD_TS;
-  const int r0 = max(2 * nv + 2 * LR, stage);
-  size_t doubles = (size_t)r0 + (size_t)(TD_THREADS / 32) * LR + 2 * (size_t)pl->nb * LR + 4 * TD_MAXNB + TD_BC +
-                   4 * TD_BC + 40 + 8;
+  const int stage = TD_KC * (pl->threads / 4 + 8 + TD_SB);
+  size_t doubles = (size_t)(2 + pl->threads / 32 + 2 * pl->nb) * LR + 4 * TD_MAXNB + TD_BC + 512 + 40 + 8 + stage;
   return doubles * sizeof(double);
 }
 
@@ -733,9 +767,13 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
   a.timing = dbg_on ? dbg : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    CHD_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
+    CHD_CUDA(cudaFuncSetAttribute(tridiag_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl->smem_optin));
+    CHD_CUDA(cudaFuncSetAttribute(tridiag_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl->smem_optin));
     attr_set = true;
   }
+  void* kfn = pl->threads == 256 ? (void*)tridiag_kernel<256> : (void*)tridiag_kernel<512>;
   if (smem > pl->smem_optin) {
     set_error("tridiag: %zu B shared memory needed, %zu available (raise ctas_per_matrix)", smem, pl->smem_optin);
     return CHD_EINVAL;
@@ -765,7 +803,7 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
       }
       CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].first, st));
     }
-    CHD_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(pl->G, cnt), dim3(TD_THREADS), params, smem, st));
+    CHD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(pl->G, cnt), dim3(pl->threads), params, smem, st));
     g_launches.fetch_add(1);
     if (g_prof_on) {
       CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].second, st));
