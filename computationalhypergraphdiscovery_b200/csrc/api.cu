@@ -139,8 +139,9 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
     return tridiag_smem_bytes(pl) <= budget;
   };
   const char* force = getenv("CHD_TD_THREADS");
+  pl->bulk = getenv("CHD_TD_BULK") ? atoi(getenv("CHD_TD_BULK")) : 0;
   pl->threads = 256;
-  bool ok = (!force || atoi(force) == 256) && fits(per_cta < pl->smem_optin ? per_cta : pl->smem_optin);
+  bool ok = (force ? atoi(force) == 256 : n <= 6144) && fits(per_cta < pl->smem_optin ? per_cta : pl->smem_optin);
   if (!ok) {
     pl->threads = 512;
     if (ctas_per_matrix <= 0 && n > 4096) pl->G = 37;
@@ -151,8 +152,17 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
     delete pl;
     return CHD_EINVAL;
   }
-  pl->wave = (pl->threads == 256 ? 2 : 1) * pl->sm_count / pl->G;
-  if (pl->wave < 1) pl->wave = 1;
+  {
+    // spread the CTA slots evenly over the matrices of a wave
+    const int slots = (pl->threads == 256 ? 2 : 1) * pl->sm_count;
+    pl->wave = slots / pl->G;
+    if (pl->wave < 1) pl->wave = 1;
+    if (ctas_per_matrix <= 0) {
+      const int Gfull = slots / pl->wave;
+      if (Gfull > pl->G && Gfull <= pl->sm_count) pl->G = Gfull;
+      (void)fits(pl->threads == 256 ? (per_cta < pl->smem_optin ? per_cta : pl->smem_optin) : pl->smem_optin);
+    }
+  }
   *plan = (chd_plan*)pl;
   return CHD_OK;
 }

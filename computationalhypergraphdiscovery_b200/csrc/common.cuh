@@ -34,6 +34,7 @@ struct Plan {
   int wave;       // matrices per cooperative launch (G * wave <= sm_count)
   int nb;         // panel width
   int threads;    // threads per CTA of the tridiagonalisation (256: two CTAs per SM, 512: one)
+  int bulk;       // symv data path: 1 = cp.async.bulk tile ring, 0 = register loads
   int rows_per_chunk;
   size_t smem_optin;
 };

@@ -24,6 +24,7 @@ constexpr int TD_MAXNB = 32;      // panel width
 constexpr int TD_BC = 128;        // max columns of B
 constexpr int TD_TN = 128;        // syr2k tile: (THREADS / 4) rows x TD_TN cols, warps of 32 x 32
 constexpr int TD_KC = 16;         // K chunk staged per pass
+constexpr int TD_NS = 2;          // stages of the symv tile ring
 constexpr int TD_SB = TD_TN + 8;  // staging stride (== 8 mod 16: conflict-free fragment loads)
 constexpr int TD_PART = 2 + 2 * TD_MAXNB + TD_BC;
 
@@ -74,6 +75,38 @@ struct GroupBarrier {
   }
 };
 
+// ---- bulk asynchronous copy (TMA engine, non-tensor form) + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
 // Row chunks of TD_RB rows are dealt to the G CTAs in zigzag order (0..G-1, G-1..0, ...) so that the
 // triangular row lengths balance across CTAs.
 __device__ __forceinline__ int chunk_row0(int ch, int g, int G) {
@@ -88,7 +121,7 @@ __device__ __forceinline__ int global_row(int lr, int g, int G) {
 // part of row c receives the reflector of column c.
 // THREADS = 256: two CTAs (of different matrices) per SM, one streams while the other sits in a barrier;
 // THREADS = 512: one CTA per SM (large n, where the per-CTA shared memory does not allow two).
-template <int TD_THREADS>
+template <int TD_THREADS, bool TD_BULK>
 __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(TridiagArgs a) {
   constexpr int TD_TM = TD_THREADS / 4;          // syr2k tile rows
   constexpr int TD_SA = TD_TM + 8;
@@ -133,11 +166,19 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
   double* Bred = cB + TD_BC;                 // 512
   double* red = Bred + 512;                  // 40
   double* sc = red + 40;                     // [0]=alpha [1]=tau [2]=beta [3]=scale [4]=vAv
-  double* Pa = sc + 8;                       // syr2k operand staging
+  uint64_t* fullbar = reinterpret_cast<uint64_t*>(sc + 8);   // TD_NS mbarriers
+  double* ring = sc + 8 + 8;                 // TD_NS x 16 x (32 NW) symv tiles; aliased by the syr2k staging
+  double* Pa = ring;
   double* Pb = Pa + TD_KC * TD_SA;
   double* ycol = mycol;                      // column part of the symv lives in this CTA's global (L2) slice
 
   GroupBarrier bar{a.bar + m, (unsigned)G, 0u};
+  int ringq = 0;
+  if (TD_BULK && tid == 0) {
+    for (int u = 0; u < TD_NS; ++u) mbar_init(&fullbar[u], 1);
+    fence_mbar_init();
+  }
+  (void)ringq;
 
   for (int i = tid; i < (2 + NW + 2 * nb) * LR; i += TD_THREADS) smem[i] = 0.0;
   __syncthreads();
@@ -217,7 +258,125 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
     TD_TICK(0)
     __syncthreads();
     double vav = 0.0;   // this lane's share of sum_j v_j * (column part of y)_j
-    // ---- symv on the stored lower triangle: 16 rows x 32 columns per warp iteration
+    // ---- symv on the stored lower triangle, two interchangeable data paths:
+    //  TD_BULK : tiles of 16 rows x (32 NW) columns are streamed into a shared-memory ring by bulk asynchronous
+    //            copies (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP), one 16 x 32 sub-block per warp;
+    //  default : every warp loads its 16 x 32 sub-blocks straight into registers (16 independent loads per
+    //            lane), no block-level synchronisation inside the product.
+    if constexpr (TD_BULK)
+    {
+      constexpr int TW = 32 * NW;
+      const int jbase = R0 & ~31;
+      const double scale_ = sc[3];
+      const int nch = LR / TD_RB;
+      auto tiles_in = [&](int ch) -> int {
+        const int i0 = chunk_row0(ch, g, G);
+        if (i0 + TD_RB - 1 < R0 || i0 >= n) return 0;
+        return (min(i0 + TD_RB - 1, n - 1) - jbase) / TW + 1;
+      };
+      int ich = 0, itt = 0, iq = ringq;   // next tile to issue (thread 0); ringq = tiles consumed so far
+      auto issue_next = [&]() {
+        while (ich < nch && itt >= tiles_in(ich)) { ++ich; itt = 0; }
+        if (ich >= nch) return;
+        const int i0 = chunk_row0(ich, g, G);
+        const int jmax = min(i0 + TD_RB - 1, n - 1);
+        const int c_lo = jbase + TW * itt;
+        const int ncols = (min(TW, jmax + 1 - c_lo) + 1) & ~1;
+        const int r_lo = max(i0, R0) - i0, r_hi = min(i0 + TD_RB, n) - i0;
+        const int st = iq % TD_NS;
+        const uint32_t bytes_row = (uint32_t)ncols * 8u;
+        fence_proxy_async();
+        mbar_expect_tx(&fullbar[st], bytes_row * (uint32_t)(r_hi - r_lo));
+        for (int r = r_lo; r < r_hi; ++r)
+          bulk_g2s(ring + ((size_t)st * TD_RB + r) * TW, A + (size_t)(i0 + r) * ldk + c_lo, bytes_row, &fullbar[st]);
+        ++itt;
+        ++iq;
+      };
+      if (tid == 0)
+        for (int u = 0; u < TD_NS; ++u) issue_next();
+      int q = ringq;   // tiles consumed so far by this CTA (mbarrier phase bookkeeping)
+      for (int ch = 0; ch < nch; ++ch) {
+        const int nt = tiles_in(ch);
+        if (nt == 0) continue;
+        const int i0 = chunk_row0(ch, g, G);
+        const int jmax = min(i0 + TD_RB - 1, n - 1);
+        double racc[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) racc[r] = 0.0;
+        for (int tt = 0; tt < nt; ++tt, ++q) {
+          const int st = q % TD_NS;
+          const uint32_t parity = (uint32_t)((q / TD_NS) & 1);
+          const int j = jbase + TW * tt + 32 * wid + lane;
+          const bool jok = (j >= R0) && (j <= jmax);
+          double vj = 0.0, yold = 0.0;
+          if (jok) {
+            vj = (j == R0) ? 1.0 : ldcg(ug + j) * scale_;
+            yold = ldcg(ycol + j);
+          }
+          mbar_wait(&fullbar[st], parity);
+          if (jbase + TW * tt + 32 * wid <= jmax) {   // warp-uniform: this sub-block has columns to process
+            const double* tp = ring + (size_t)st * TD_RB * TW + 32 * wid + lane;
+            double colacc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const int i = i0 + r;
+              const bool ok = jok && (i >= R0) && (i < n) && (j <= i);
+              const double av = ok ? tp[r * TW] : 0.0;
+              racc[r] = fma(av, vj, racc[r]);
+              if (j < i) colacc = fma(av, vloc[ch * TD_RB + r], colacc);
+            }
+            if (jok) {
+              ycol[j] = yold + colacc;
+              vav = fma(vj, colacc, vav);
+            }
+          }
+          __syncthreads();
+          if (tid == 0) issue_next();
+        }
+        // butterfly reduction of the 16 row accumulators over the warp (16 shuffles)
+        double t8[8], t4[4], t2[2], t1;
+        {
+          const bool hi = lane & 16;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const double send = hi ? racc[r] : racc[r + 8];
+            const double keep = hi ? racc[r + 8] : racc[r];
+            t8[r] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+        }
+        {
+          const bool hi = lane & 8;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double send = hi ? t8[r] : t8[r + 4];
+            const double keep = hi ? t8[r + 4] : t8[r];
+            t4[r] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+        }
+        {
+          const bool hi = lane & 4;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const double send = hi ? t4[r] : t4[r + 2];
+            const double keep = hi ? t4[r + 2] : t4[r];
+            t2[r] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+        {
+          const bool hi = lane & 2;
+          const double send = hi ? t2[0] : t2[1];
+          const double keep = hi ? t2[1] : t2[0];
+          t1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+        if ((lane & 1) == 0) {
+          const int r = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          rowpart[wid * LR + ch * TD_RB + r] = t1;
+        }
+      }
+      ringq = q;
+    }
+    else
     {
       const int jbase = R0 & ~31;
       const double scale_ = sc[3];
@@ -717,7 +876,9 @@ size_t tridiag_smem_bytes(const Plan* pl) {
   const int chunks = (pl->n + TD_RB - 1) / TD_RB;
   const int LR = (chunks + pl->G - 1) / pl->G * TD_RB;
   const int stage = TD_KC * (pl->threads / 4 + 8 + TD_SB);
-  size_t doubles = (size_t)(2 + pl->threads / 32 + 2 * pl->nb) * LR + 4 * TD_MAXNB + TD_BC + 512 + 40 + 8 + stage;
+  const int ring = pl->bulk ? TD_NS * TD_RB * pl->threads : 0;   // TD_NS x 16 rows x (32 * warps) columns
+  size_t doubles = (size_t)(2 + pl->threads / 32 + 2 * pl->nb) * LR + 4 * TD_MAXNB + TD_BC + 512 + 40 + 8 + 8 +
+                   (size_t)max(stage, ring);
   return doubles * sizeof(double);
 }
 
@@ -767,13 +928,14 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
   a.timing = dbg_on ? dbg : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
-    CHD_CUDA(cudaFuncSetAttribute(tridiag_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->smem_optin));
-    CHD_CUDA(cudaFuncSetAttribute(tridiag_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->smem_optin));
+    void* fns[4] = {(void*)tridiag_kernel<256, false>, (void*)tridiag_kernel<512, false>,
+                    (void*)tridiag_kernel<256, true>, (void*)tridiag_kernel<512, true>};
+    for (void* f : fns)
+      CHD_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
     attr_set = true;
   }
-  void* kfn = pl->threads == 256 ? (void*)tridiag_kernel<256> : (void*)tridiag_kernel<512>;
+  void* kfn = pl->bulk ? (pl->threads == 256 ? (void*)tridiag_kernel<256, true> : (void*)tridiag_kernel<512, true>)
+                       : (pl->threads == 256 ? (void*)tridiag_kernel<256, false> : (void*)tridiag_kernel<512, false>);
   if (smem > pl->smem_optin) {
     set_error("tridiag: %zu B shared memory needed, %zu available (raise ctas_per_matrix)", smem, pl->smem_optin);
     return CHD_EINVAL;

@@ -88,8 +88,14 @@ def test_cross_gram_and_predict():
             np.testing.assert_allclose(out[t], ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
 
 
-@pytest.mark.parametrize("n,G", [(97, 2), (200, 4), (310, 8), (256, 3)])
-def test_tridiag_matches_householder_model(n, G):
+@pytest.mark.parametrize("n,G,threads,bulk", [(97, 2, 0, 0), (200, 4, 0, 0), (310, 8, 0, 0), (256, 3, 0, 0),
+                                               (333, 5, 256, 1), (290, 4, 512, 0), (301, 6, 512, 1), (1100, 0, 0, 0)])
+def test_tridiag_matches_householder_model(n, G, threads, bulk, monkeypatch):
+    """(threads, bulk) select the kernel variant: 256 threads x 2 CTAs/SM or 512 x 1, register or
+    cp.async.bulk (UBLKCP) symv data path; 0 = the plan's default."""
+    if threads:
+        monkeypatch.setenv("CHD_TD_THREADS", str(threads))
+    monkeypatch.setenv("CHD_TD_BULK", str(bulk))
     nat = _native()
     N = 6
     X, _ = _data(n, N, 6)
