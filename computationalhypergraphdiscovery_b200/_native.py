@@ -39,6 +39,7 @@ _SIGNATURES = {
     "chd_plan_destroy": (None, [_vp]),
     "chd_workspace_bytes": (_sz, [_vp, _i]),
     "chd_plan_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "chd_plan_tuning": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "chd_normal": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "chd_split": (_i, [_vp, _i, _vp, _vp, _vp]),
     "chd_gram": (_i, [_vp, ctypes.POINTER(KernelDesc), _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _sz, _vp]),
@@ -124,6 +125,8 @@ class Plan:
         g, w, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         _check(lib.chd_plan_info(h, ctypes.byref(g), ctypes.byref(w), ctypes.byref(s)), "chd_plan_info")
         self.ctas_per_matrix, self.matrices_per_wave, self.sm_count = g.value, w.value, s.value
+        _check(lib.chd_plan_tuning(h, ctypes.byref(g), ctypes.byref(w), ctypes.byref(s)), "chd_plan_tuning")
+        self.panel_width, self.threads_per_cta, self.bulk_symv = g.value, w.value, s.value
         self.ldk = (self.n + 1) // 2 * 2
         self.grid = torch.from_numpy(gamma_grid_host()).to(self.device)
         self._ws = None

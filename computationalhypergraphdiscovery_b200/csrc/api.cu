@@ -178,6 +178,15 @@ extern "C" int chd_plan_info(const chd_plan* plan, int* ctas_per_matrix, int* ma
   return CHD_OK;
 }
 
+extern "C" int chd_plan_tuning(const chd_plan* plan, int* panel_width, int* threads_per_cta, int* bulk_symv) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl) return CHD_EINVAL;
+  if (panel_width) *panel_width = pl->nb;
+  if (threads_per_cta) *threads_per_cta = pl->threads;
+  if (bulk_symv) *bulk_symv = pl->bulk;
+  return CHD_OK;
+}
+
 extern "C" size_t chd_workspace_bytes(const chd_plan* plan, int T) {
   const Plan* pl = (const Plan*)plan;
   if (!pl || T <= 0) return 0;

@@ -67,6 +67,9 @@ void chd_plan_destroy(chd_plan* plan);
 /* Bytes of scratch the batched calls below need for T targets in flight. */
 size_t chd_workspace_bytes(const chd_plan* plan, int T);
 int chd_plan_info(const chd_plan* plan, int* ctas_per_matrix, int* matrices_per_wave, int* sm_count);
+/* Tuning of the tridiagonalisation kernel: panel width, threads per CTA (256: two CTAs per SM, 512: one),
+ * symv data path (1: cp.async.bulk tile ring, 0: register loads). */
+int chd_plan_tuning(const chd_plan* plan, int* panel_width, int* threads_per_cta, int* bulk_symv);
 
 /* jax.random.normal(key, (rows, cols)) for T keys (interpolatory.py:99):
  * out[t][r][c], leading dimension ld >= cols. */
