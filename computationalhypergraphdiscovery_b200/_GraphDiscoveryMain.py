@@ -188,6 +188,11 @@ class GraphDiscovery:
         targets = parallel.shard_targets(all_targets, rank, world)
         pos = {name: i for i, name in enumerate(all_targets)}
         subkeys = subkeys_all[[pos[t] for t in targets]] if targets else subkeys_all[:0]
+        if world > 1 and not targets:
+            # more ranks than targets: nothing to compute here, but take part in the two collectives
+            parallel.all_gather_list([-1] * len(self.kernels))
+            parallel.merge_node_results(self.G, parallel.all_gather_results({}))
+            return
         gas_idx, w0 = self._prepare_modes_for_ancestor_finding(targets)
 
         kernel_performance, stage1_dev = self.get_kernel_performance(w0, gas_idx, subkeys)

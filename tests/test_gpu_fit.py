@@ -121,3 +121,84 @@ def test_algebraic_golden(golden_dir, ex):
         node = gd.G.nodes["$" + short + "$"]
         assert f"{node['gamma']:.3g}" == d["gamma_3sf"], (short, node["gamma"])
         assert f"{node['noise']:.3g}" == d["noise_3sf"], (short, node["noise"])
+
+
+def test_clusters_possible_edges_and_threshold_choosers():
+    """Config-2 style workflow: clusters + possible_edges + scaled kernels + threshold choosers."""
+    import networkx as nx
+    import computationalhypergraphdiscovery_b200 as CHD
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    X, names = make_data(260, 9, seed=3)
+    clusters = [names[0:3], names[3:5], names[5:6], names[6:9]]
+    rng = np.random.default_rng(4)
+    pe = nx.DiGraph()
+    pe.add_nodes_from(names)
+    for a in names:
+        for b in names:
+            if a != b and rng.random() > 0.2:
+                pe.add_edge(a, b)
+    kernels = [0.5 * CHD.Modes.LinearMode(), 0.5 * CHD.Modes.QuadraticMode(), 0.7 * CHD.Modes.GaussianMode(l=1.5)]
+    gd = CHD.GraphDiscovery(X, names, kernels=kernels, clusters=clusters, possible_edges=pe, verbose=False,
+                            gamma_min=1e-8)
+    gd.fit(kernel_chooser=CHD.decision.ThresholdKernelChooser(0.9), mode_chooser=CHD.decision.ThresholdModeChooser(0.5))
+    adj = np.array(nx.adjacency_matrix(pe, nodelist=names).todense())
+    res = ochd.fit(X, names, kernels=[("linear", 0.5, None), ("quadratic", 0.5, None), ("gaussian", 0.7, 1.5)],
+                   clusters=clusters, adjacency=adj, gamma_min=1e-8, kernel_chooser=("threshold", 0.9),
+                   mode_chooser=("threshold", 0.5))
+    _compare_with_oracle(gd, res, names, {})
+
+
+def test_loop_number_zero_two_clusters():
+    """C = 2 clusters -> no prune step, activations of the full set only (MAIN:662-691)."""
+    import computationalhypergraphdiscovery_b200 as CHD
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    X, names = make_data(150, 4, seed=5)
+    clusters = [names[:2], names[2:]]
+    gd = CHD.GraphDiscovery(X, names, clusters=clusters, verbose=False)
+    gd.fit()
+    res = ochd.fit(X, names, clusters=clusters)
+    _compare_with_oracle(gd, res, names, {})
+
+
+def test_predict_and_pickle_roundtrip():
+    import pickle
+    import computationalhypergraphdiscovery_b200 as CHD
+    from oracle import kernels as okern
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    X, names = make_data(220, 6, seed=6)
+    gd = _fit_cuda(X, names)
+    Xq, _ = make_data(57, 6, seed=7)
+    pred = gd.predict(names, Xq)
+    specs = okern.make_specs([("linear", 2.0, None), ("quadratic", 1.0, None), ("gaussian", 1.0, 1.0)])
+    Xn = (X - X.mean(0)) / X.std(0)
+    Xqn = (Xq - X.mean(0)) / X.std(0)
+    for j, name in enumerate(names):
+        node = gd.G.nodes[name]
+        if "kernel_index" not in node:
+            ref = np.zeros(57) * X.std(0)[j] + X.mean(0)[j]
+        else:
+            K = okern.gram(specs[node["kernel_index"]], Xqn, Xn, np.asarray(node["active_modes"], dtype=float))
+            ref = (K @ (-node["coeff"])) * X.std(0)[j] + X.mean(0)[j]
+        np.testing.assert_allclose(pred[:, j], ref, rtol=1e-9, atol=1e-9)
+    gd2 = pickle.loads(pickle.dumps(gd))
+    assert sorted(gd2.G.edges) == sorted(gd.G.edges)
+    np.testing.assert_allclose(gd2.predict(names, Xq), pred, rtol=1e-12, atol=1e-12)
+    new = gd2.prepare_new_graph_with_clusters([names[:3], names[3:]])
+    new.print_func = lambda *a, **k: None
+    new.fit()
+    assert new.G.number_of_nodes() == 6
+
+
+def test_targets_subset_keeps_full_run_subkeys():
+    """fit(targets=subset) uses split(key, len(targets)+1) like the reference (MAIN:311)."""
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    import computationalhypergraphdiscovery_b200 as CHD
+    X, names = make_data(180, 6, seed=8)
+    gd = CHD.GraphDiscovery(X, names, verbose=False)
+    gd.fit(targets=names[1:4], key=CHD.random.PRNGKey(7))
+    from oracle import jaxprng
+    res = ochd.fit(X, names, targets=names[1:4], key=jaxprng.PRNGKey(7))
+    st = gd.last_fit["stage1"]
+    np.testing.assert_allclose(st[1], res["stage1"]["noises"], rtol=1e-8)
+    np.testing.assert_allclose(st[2], res["stage1"]["Z_lows"], rtol=1e-8)
+    assert (gd.last_fit["chosen_kernel"] == res["chosen_kernel"]).all()
