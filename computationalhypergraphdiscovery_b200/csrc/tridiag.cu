@@ -805,6 +805,7 @@ __global__ void __launch_bounds__(512) backtransform_kernel(BackArgs a) {
   double* x = smem;            // n
   double* cc = x + n;          // nb
   double* ss = cc + TD_MAXNB;  // nb
+  double* gg = ss + TD_MAXNB;  // nb x nb panel Gram block
   for (int i = tid; i < n; i += blockDim.x) x[i] = a.x[(size_t)m * n + i];
   __syncthreads();
   // columns c = -1..n-2 live in panels [-1, nb-2], [nb-1, 2nb-2], ...
@@ -813,12 +814,26 @@ __global__ void __launch_bounds__(512) backtransform_kernel(BackArgs a) {
   for (int pnl = npanel - 1; pnl >= 0; --pnl) {
     const int cfirst = -1 + pnl * nb;
     const int kp = min(nb, ncol - pnl * nb);
-    // c_t = v_t . x  (rows > c_t)
+    // panel Gram block (v_t2 . v_t, t < t2) -> shared memory, so that the short recurrence below is not a chain
+    // of dependent global loads
+    for (int q = tid; q < kp * kp; q += blockDim.x) {
+      const int t2 = q / kp, t = q % kp;
+      gg[t2 * TD_MAXNB + t] = (t < t2) ? pg[(size_t)(cfirst + t2 + 1) * nb + t] : 0.0;
+    }
+    // c_t = v_t . x  (rows > c_t): one warp per reflector, 8 independent loads per lane in flight
     for (int t = wid; t < kp; t += nw) {
       const int c = cfirst + t;
       const double* vr = (c < 0) ? v0 : (A + (size_t)c * ldk);
       double s = 0.0;
-      for (int i = c + 1 + lane; i < n; i += 32) s += vr[i] * x[i];
+      int i = c + 1 + lane;
+      for (; i + 7 * 32 < n; i += 8 * 32) {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = vr[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = fma(r[u], x[i + 32 * u], s);
+      }
+      for (; i < n; i += 32) s = fma(vr[i], x[i], s);
       s = warp_sum(s);
       if (lane == 0) cc[t] = s;
     }
@@ -826,19 +841,23 @@ __global__ void __launch_bounds__(512) backtransform_kernel(BackArgs a) {
     if (tid == 0) {
       for (int t = kp - 1; t >= 0; --t) {
         double s = cc[t];
-        for (int t2 = t + 1; t2 < kp; ++t2) s -= pg[(size_t)(cfirst + t2 + 1) * nb + t] * ss[t2];
+        for (int t2 = t + 1; t2 < kp; ++t2) s -= gg[t2 * TD_MAXNB + t] * ss[t2];
         ss[t] = tau[cfirst + t + 1] * s;
       }
     }
     __syncthreads();
     for (int i = cfirst + 1 + tid; i < n; i += blockDim.x) {
       double s = x[i];
-      for (int t = 0; t < kp; ++t) {
-        const int c = cfirst + t;
-        if (i > c) {
-          const double* vr = (c < 0) ? v0 : (A + (size_t)c * ldk);
-          s -= ss[t] * vr[i];
+      for (int t0 = 0; t0 < kp; t0 += 8) {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int t = t0 + u, c = cfirst + t;
+          r[u] = (t < kp && i > c) ? ((c < 0) ? v0[i] : A[(size_t)c * ldk + i]) : 0.0;
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t0 + u < kp) s = fma(-ss[t0 + u], r[u], s);
       }
       x[i] = s;
     }
@@ -989,7 +1008,7 @@ int backtransform_launch(const Plan* pl, const double* K, int ldk, const Tridiag
   BackArgs a;
   a.K = K; a.strideK = (size_t)pl->n * ldk; a.ldk = ldk; a.v0 = tb.v0; a.tau = tb.tau; a.pgram = tb.pgram;
   a.x = x; a.beta0 = beta0; a.out = out; a.out_stride = out_stride; a.n = pl->n; a.nb = pl->nb;
-  const size_t smem = ((size_t)pl->n + 2 * TD_MAXNB + 8) * sizeof(double);
+  const size_t smem = ((size_t)pl->n + 2 * TD_MAXNB + TD_MAXNB * TD_MAXNB + 8) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     CHD_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
