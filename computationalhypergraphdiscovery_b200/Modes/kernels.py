@@ -40,14 +40,26 @@ class ModeKernel:
     def __rmul__(self, other):
         return self.__mul__(other)
 
-    # --- native side
+    # --- extension hook (KERN:7-68): a user subclass provides `name`, `_scale`, `_is_interpolatory`,
+    # `_memory_efficient_required`, `setup(X, scales)` and `kernel(X, Y, which_dim)` (NumPy in, NumPy out);
+    # it is served by the generic path: host-provided Gram -> chd_regress, activations through
+    # `individual_influence` (default: whole kernel minus the kernel without the cluster, KERN:39-56).
+    def individual_influence(self, X, Y, which_dim, which_dim_only):
+        whole_k = self(X, Y, which_dim)
+        rest = which_dim * (1 - which_dim_only)
+        rest_k = self(X, Y, rest)
+        return whole_k - rest_k
+
+    def __call__(self, X, Y, which_dim):
+        return self.kernel(X, Y, which_dim)
+
     def setup(self, X, scales):
         raise NotImplementedError
 
     @property
     def desc(self):
-        """chd_kernel_desc for the CUDA library (valid after setup())."""
-        return self._desc
+        """chd_kernel_desc for the CUDA library (built-in modes, valid after setup()); None for user kernels."""
+        return getattr(self, "_desc", None)
 
 
 class LinearMode(ModeKernel):

@@ -293,7 +293,7 @@ class GraphDiscovery:
         for ki, kernel in enumerate(self.kernels):
             for s in range(0, T, bs):
                 sl = slice(s, min(T, s + bs))
-                K = plan.gram(kernel.desc, self._Xd, w0_d[sl].contiguous())
+                K = self._gram(kernel, w0_d[sl].contiguous(), w0[sl])
                 gmin = torch.full((sl.stop - sl.start,), float(self.gamma_min), dtype=torch.float64, device=dev)
                 r = plan.regress(K, ga_all[sl].contiguous(), keys_d[sl].contiguous(), gmin, mode=1,
                                  base=float(self.gamma_min))
@@ -316,6 +316,75 @@ class GraphDiscovery:
         perf = (ybs.cpu().numpy(), noises, outs["z_low"].cpu().numpy(), outs["z_high"].cpu().numpy(), gam,
                 keys_out.cpu().numpy().astype(np.uint32))
         return perf, dict(lambda_min=outs["lambda_min"].cpu().numpy())
+
+    # ------------------------------------------------------------------ user-defined kernels (generic path)
+    def _gram(self, kernel, w_dev, w_host):
+        """(T, n, ldk) Gram matrices: CUDA for the built-in modes, host-provided for user ModeKernels."""
+        plan = self._device()
+        if kernel.desc is not None:
+            return plan.gram(kernel.desc, self._Xd, w_dev)
+        T, n = w_host.shape[0], plan.n
+        K = torch.zeros((T, n, plan.ldk), dtype=torch.float64, device=plan.device)
+        for t in range(T):
+            Kt = np.asarray(kernel(self.X, self.X, w_host[t].astype(np.float64)), dtype=np.float64)
+            K[t, :, :n] = torch.from_numpy(np.ascontiguousarray(Kt)).to(plan.device)
+        return K
+
+    def _custom_activations(self, kernel, yb, ga, w_vars, alive):
+        """HELP:113-132 for one target on the host: yb^T Infl_c yb / energy, 2.0 for empty rows."""
+        im = self.modes.index_matrix
+        energy = -float(np.dot(ga, yb))
+        act = np.full(im.shape[0], 2.0)
+        w = w_vars.astype(np.float64)
+        for c in range(im.shape[0]):
+            w_c = im[c] * w * float(alive[c])
+            if not w_c.any():
+                continue
+            M = np.asarray(kernel.individual_influence(self.X, self.X, w, w_c))
+            act[c] = float(yb @ (M @ yb)) / energy
+        return act
+
+    def _custom_chain(self, kernel, b, w0_host, first_step, nsteps):
+        """Prune steps for a user ModeKernel: host-orchestrated (activations + Gram on the host,
+        regression / gamma search / Z-test in chd_regress).  Same outputs as Plan.prune_chain."""
+        plan = self._device()
+        dev, f64 = plan.device, torch.float64
+        tb, n, N, C = w0_host.shape[0], plan.n, plan.N, len(self.modes.clusters)
+        cluster_of = self.modes.cluster_of
+        out = dict(pruned=torch.empty((tb, nsteps), dtype=torch.int32, device=dev),
+                   act=torch.empty((tb, nsteps, C), dtype=f64, device=dev),
+                   yb=torch.empty((tb, nsteps, n), dtype=f64, device=dev))
+        for k in ("noise", "z_low", "z_high", "gamma"):
+            out[k] = torch.empty((tb, nsteps), dtype=f64, device=dev)
+        ga_h = b["ga"].cpu().numpy()
+        for s in range(nsteps):
+            step = first_step + s
+            p = N - step - 1
+            if step % 50 == 0 or (p * (p + 1)) / 2 == N:                   # MAIN:622-631
+                lm = b["lmin"]
+                b["gmin"].copy_(torch.where(lm + 1e-9 < 0, -2 * lm, torch.full_like(lm, 1e-9)))
+            yb_h, alive_h = b["yb"].cpu().numpy(), b["alive"].cpu().numpy()
+            acts = np.empty((tb, C))
+            pr = np.empty(tb, dtype=np.int32)
+            for t in range(tb):
+                w_vars = w0_host[t] * alive_h[t][cluster_of]
+                acts[t] = self._custom_activations(kernel, yb_h[t], ga_h[t], w_vars, alive_h[t])
+                nan = np.isnan(acts[t])
+                pr[t] = int(np.argmax(nan)) if nan.any() else int(np.argmin(acts[t]))
+                alive_h[t, pr[t]] = 0
+            b["alive"].copy_(torch.from_numpy(alive_h).to(dev))
+            w_new = (w0_host * alive_h[:, cluster_of]).astype(np.uint8)
+            K = self._gram(kernel, None, w_new)
+            r = plan.regress(K, b["ga"], b["keys"], b["gmin"], mode=0)
+            b["yb"].copy_(r["yb"])
+            b["keys"].copy_(r["keys"])
+            b["lmin"].copy_(r["lambda_min"])
+            out["pruned"][:, s] = torch.from_numpy(pr).to(dev)
+            out["act"][:, s] = torch.from_numpy(acts).to(dev)
+            out["yb"][:, s] = r["yb"]
+            for k in ("noise", "z_low", "z_high", "gamma"):
+                out[k][:, s] = r[k]
+        return out
 
     def choose_kernel(kernel_performances, kernel_chooser):
         """Per-node kernel choice (MAIN:513-557)."""
@@ -372,12 +441,21 @@ class GraphDiscovery:
         if loop_number == 0:
             # MAIN:662-691: no prune step, but the activations of the full set are still needed
             for b in batches:
+                if kernel.desc is None:
+                    ybh, gah, alh = b["yb"].cpu().numpy(), b["ga"].cpu().numpy(), b["alive"].cpu().numpy()
+                    w0b = w0[b["sl"]]
+                    b["act0"] = np.stack([self._custom_activations(kernel, ybh[t], gah[t], w0b[t], alh[t])
+                                          for t in range(w0b.shape[0])])[:, None, :]
+                    continue
                 act, _ = plan.activations(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"], b["yb"],
                                           b["ga"], False)
                 b["act0"] = act.cpu().numpy()[:, None, :]
         else:
             def run(nsteps):
                 for b in batches:
+                    if kernel.desc is None:
+                        b["outs"].append(self._custom_chain(kernel, b, w0[b["sl"]], done, nsteps))
+                        continue
                     b["outs"].append(plan.prune_chain(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"],
                                                       b["ga"], b["yb"], b["keys"], b["lmin"], b["gmin"], done, nsteps,
                                                       keep_yb=True))
@@ -536,6 +614,12 @@ class GraphDiscovery:
         for i, kernel in enumerate(self.kernels):
             mask = kernels == i
             if not np.any(mask):
+                continue
+            if kernel.desc is None:   # user ModeKernel: host-provided cross-Gram
+                cols = np.nonzero(mask)[0]
+                for ci, am, yb_t in zip(cols, active_modess[mask], ybs[mask]):
+                    K = np.asarray(kernel(X_pred_used, self.X, (am != 0).astype(np.float64)))
+                    res[:, ci] = K @ (-yb_t)
                 continue
             w = torch.from_numpy(np.ascontiguousarray(active_modess[mask] != 0).astype(np.uint8)).to(dev)
             yb = torch.from_numpy(np.ascontiguousarray(ybs[mask])).to(dev)

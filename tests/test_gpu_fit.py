@@ -207,3 +207,41 @@ def test_targets_subset_keeps_full_run_subkeys():
     np.testing.assert_allclose(st[1], res["stage1"]["noises"], rtol=1e-8)
     np.testing.assert_allclose(st[2], res["stage1"]["Z_lows"], rtol=1e-8)
     assert (gd.last_fit["chosen_kernel"] == res["chosen_kernel"]).all()
+
+
+def test_custom_mode_kernel_extension_hook():
+    """A user ModeKernel (NumPy `kernel(X, Y, which_dim)`, KERN:7-68) goes through the generic path and must
+    reproduce the built-in quadratic mode it re-implements."""
+    import computationalhypergraphdiscovery_b200 as CHD
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+
+    class MyQuadratic(CHD.Modes.ModeKernel):
+        def __init__(self):
+            super().__init__()
+            self.name = "myquad"
+            self._is_interpolatory = False
+            self._memory_efficient_required = False
+
+        def setup(self, X, scales):
+            assert self.scale == scales[self.name]
+            self.alpha = 0.5 * 2.0 / self.scale
+
+        def kernel(self, X, Y, which_dim):
+            L = (X * which_dim[None, :]) @ Y.T
+            return self.scale * (self.alpha + L) ** 2 + (1 - self.alpha ** 2 * self.scale)
+
+    X, names = make_data(200, 6, seed=9)
+    ref = CHD.GraphDiscovery(X, names, kernels=[CHD.Modes.QuadraticMode()], verbose=False)
+    ref.fit()
+    gd = CHD.GraphDiscovery(X, names, kernels=[MyQuadratic()], verbose=False)
+    gd.fit()
+    assert sorted(gd.G.edges) == sorted(ref.G.edges)
+    np.testing.assert_allclose(gd.last_fit["stage1"][1], ref.last_fit["stage1"][1], rtol=1e-9)
+    for k in ref.last_fit["chains"]:
+        np.testing.assert_allclose(gd.last_fit["chains"][k]["noises"], ref.last_fit["chains"][k]["noises"], rtol=1e-7)
+        m = ref.last_fit["chains"][k]["activations"] != 2.0
+        np.testing.assert_allclose(gd.last_fit["chains"][k]["activations"][m],
+                                   ref.last_fit["chains"][k]["activations"][m], rtol=1e-7)
+    for nm in names:
+        if "type" in gd.G.nodes[nm]:
+            assert gd.G.nodes[nm]["type"] == "myquad"
