@@ -256,13 +256,15 @@ def run_b200(args):
         gmin = torch.full((Tb,), 1e-9, dtype=torch.float64, device=dev)
         r = plan.regress(K, ga, keys, gmin, mode=1, base=1e-9)
         del K
+        p_cache = (dict(P=torch.empty((Tb, n, plan.ldk), dtype=torch.float64, device=dev), valid=0)
+                   if kernel == "gaussian" else None)
         return dict(desc=desc, w0=w0d, ga=ga, alive=torch.ones((Tb, N), dtype=torch.uint8, device=dev),
                     yb=r["yb"], keys=r["keys"], lmin=r["lambda_min"],
-                    gmin=torch.full((Tb,), 1e-9, dtype=torch.float64, device=dev), step=0)
+                    gmin=torch.full((Tb,), 1e-9, dtype=torch.float64, device=dev), step=0, p_cache=p_cache)
 
     def chain_step(st):
         out = plan.prune_chain(st["desc"], Xd, cl, st["w0"], st["alive"], st["ga"], st["yb"], st["keys"], st["lmin"],
-                               st["gmin"], st["step"], 1, keep_yb=True)
+                               st["gmin"], st["step"], 1, keep_yb=True, p_cache=st["p_cache"])
         st["step"] += 1
         return out
 
@@ -359,7 +361,7 @@ def run_b200(args):
             d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             h2d += sum(v.numel() * v.element_size() for v in host.values())
             out = plan.prune_chain(s_["desc"], Xs, cl, d["w0"], d["alive"], d["ga"], d["yb"], d["keys"], d["lmin"],
-                                   d["gmin"], s_["step"], 1, keep_yb=True)
+                                   d["gmin"], s_["step"], 1, keep_yb=True, p_cache=s_["p_cache"])
             s_["step"] += 1
             for k in ("pruned", "noise", "z_low", "z_high", "gamma", "act", "yb", "status"):
                 res_h[k] = out[k].cpu()

@@ -160,7 +160,7 @@ class GraphDiscovery:
         plan = self._device()
         free, _total = torch.cuda.mem_get_info(plan.device)
         held = plan._ws.numel() if plan._ws is not None else 0
-        per = plan.workspace_bytes(1) + 8 * plan.n * plan.ldk
+        per = plan.workspace_bytes(1) + 2 * 8 * plan.n * plan.ldk   # + Gram output / Gaussian product-map cache
         return int(max(1, min(T, (0.7 * (free + held)) // per)))
 
     # ------------------------------------------------------------------ fit
@@ -436,7 +436,10 @@ class GraphDiscovery:
                 yb=torch.from_numpy(np.ascontiguousarray(ybs_kernel[sl])).to(dev),
                 keys=torch.from_numpy(subkeys_kernel[sl].astype(np.uint32).view(np.int32).copy()).to(dev),
                 lmin=torch.from_numpy(np.ascontiguousarray(lambda_min_kernel[sl])).to(dev),
-                gmin=torch.full((tb,), 1e-9, dtype=torch.float64, device=dev), ga=ga[sl].contiguous(), outs=[]))
+                gmin=torch.full((tb,), 1e-9, dtype=torch.float64, device=dev), ga=ga[sl].contiguous(), outs=[],
+                # Gaussian mode: product map prod(1 + E_d) carried from step to step (one division per prune)
+                p_cache=(dict(P=torch.empty((tb, n, plan.ldk), dtype=torch.float64, device=dev), valid=0)
+                         if kernel.desc is not None and kernel.desc.kind == _native.KERNEL_GAUSSIAN else None)))
         done = 0
         if loop_number == 0:
             # MAIN:662-691: no prune step, but the activations of the full set are still needed
@@ -458,7 +461,7 @@ class GraphDiscovery:
                         continue
                     b["outs"].append(plan.prune_chain(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"],
                                                       b["ga"], b["yb"], b["keys"], b["lmin"], b["gmin"], done, nsteps,
-                                                      keep_yb=True))
+                                                      keep_yb=True, p_cache=b["p_cache"]))
             run(steps_planned)
             done = steps_planned
             # The reference keeps stepping until every mask of the group is empty or L steps are done

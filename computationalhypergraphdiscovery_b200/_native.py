@@ -48,7 +48,7 @@ _SIGNATURES = {
     "chd_activations": (_i, [_vp, ctypes.POINTER(KernelDesc), _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp,
                              _sz, _vp]),
     "chd_prune_chain": (_i, [_vp, ctypes.POINTER(KernelDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
-                             _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                             _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i), _vp, _vp, _sz, _vp]),
     "chd_predict": (_i, [_vp, ctypes.POINTER(KernelDesc), _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "chd_tridiag": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "chd_dmma_peak": (_i, [_i, ctypes.POINTER(_d)]),
@@ -216,8 +216,9 @@ class Plan:
         return act, pruned
 
     def prune_chain(self, desc, X, cluster_of, w0, alive, ga, yb, keys, lambda_min, gamma_min, first_step, steps,
-                    keep_yb=True):
-        """Runs `steps` prune steps device-resident; state tensors are updated in place."""
+                    keep_yb=True, p_cache=None):
+        """Runs `steps` prune steps device-resident; state tensors are updated in place.
+        p_cache: optional dict {"P": (T, n, ldk) tensor, "valid": 0/1} carrying the Gaussian product map."""
         T = w0.shape[0]
         dev, f64 = self.device, torch.float64
         S = max(int(steps), 1)
@@ -230,12 +231,16 @@ class Plan:
         if steps <= 0:
             return out
         ws = self.workspace(T)
+        pv = ctypes.c_int(int(p_cache["valid"])) if p_cache else None
         _check(load().chd_prune_chain(self._h, ctypes.byref(desc), _ptr(X), _ptr(cluster_of), _ptr(w0), _ptr(alive),
                                       _ptr(ga), _ptr(yb), _ptr(keys), _ptr(self.grid), _ptr(lambda_min),
                                       _ptr(gamma_min), T, int(first_step), int(steps), _ptr(out["pruned"]),
                                       _ptr(out["noise"]), _ptr(out["z_low"]), _ptr(out["z_high"]), _ptr(out["gamma"]),
-                                      _ptr(out["act"]), _ptr(out["yb"]), _ptr(out["status"]), _ptr(ws), ws.numel(),
-                                      _stream()), "chd_prune_chain")
+                                      _ptr(out["act"]), _ptr(out["yb"]),
+                                      _ptr(p_cache["P"]) if p_cache else None, ctypes.byref(pv) if p_cache else None,
+                                      _ptr(out["status"]), _ptr(ws), ws.numel(), _stream()), "chd_prune_chain")
+        if p_cache:
+            p_cache["valid"] = pv.value
         return out
 
     def predict(self, desc, X, Xq, w, yb):

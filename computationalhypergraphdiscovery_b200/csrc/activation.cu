@@ -31,6 +31,18 @@ int active_vars_launch(const uint8_t* w0, const uint8_t* alive, const int32_t* c
   return CHD_OK;
 }
 
+__global__ void removed_vars_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int count,
+                                    uint8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (a[i] && !b[i]) ? 1 : 0;
+}
+
+int removed_vars_launch(const uint8_t* w_prev, const uint8_t* w_new, int count, uint8_t* wrem, cudaStream_t st) {
+  removed_vars_kernel<<<(count + 255) / 256, 256, 0, st>>>(w_prev, w_new, count, wrem);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
 // gdot[t][d] = sum_i X[i][d] yb[t][i];  energy[t] = -sum_i ga[t][i] yb[t][i]
 __global__ void __launch_bounds__(256) gdot_kernel(const double* __restrict__ X, int n, int N,
                                                    const double* __restrict__ yb, const double* __restrict__ ga,
@@ -134,7 +146,8 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
                                                           const uint8_t* __restrict__ w,
                                                           const int32_t* __restrict__ mem_off,
                                                           const int32_t* __restrict__ mem_idx, double inv2l2,
-                                                          double* __restrict__ partial, int nblk) {
+                                                          double* __restrict__ partial, int nblk,
+                                                          const double* __restrict__ Pc, int ldk) {
   extern __shared__ double sacc[];  // C x 8 warps
   const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
@@ -160,7 +173,15 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
         const int i = i0 + a, j = j0 + b;
         yy[a][b] = (i < n && j < n) ? sym * y[i] * y[j] : 0.0;
       }
-    for (int d = 0; d < N; ++d) {
+    if (Pc) {   // cached product map of the current mask: no first pass
+      const double* Pm = Pc + (size_t)t * n * ldk;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (i0 + a < n && j0 + b < n) P[a][b] = Pm[(size_t)(i0 + a) * ldk + j0 + b];
+    }
+    for (int d = 0; d < N && !Pc; ++d) {
       if (!wt[d]) continue;
       const double* xr = XT + (size_t)d * n;
       double xi[4], xj[4];
@@ -346,7 +367,7 @@ size_t act_workspace(const Plan* pl, int T) {
 int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const int32_t* cluster_of,
                const uint8_t* w0, uint8_t* alive, const double* yb, const double* ga, int T, double* act,
                size_t act_stride, int prune, int32_t* pruned, size_t pruned_stride, void* ws, size_t ws_bytes,
-               cudaStream_t st) {
+               cudaStream_t st, const double* P, int ldk) {
   const int n = pl->n, N = pl->N, C = pl->C;
   Carver cv(ws, ws_bytes);
   uint8_t* w = cv.take<uint8_t>((size_t)T * N);
@@ -391,7 +412,7 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
       attr_set = true;
     }
     gauss_pairs_kernel<<<dim3(nblk, T), 256, smem, st>>>(XT, n, N, C, yb, w, mem_off, mem_idx,
-                                                         1.0 / (2.0 * kd->l * kd->l), gpart, nblk);
+                                                         1.0 / (2.0 * kd->l * kd->l), gpart, nblk, P, ldk);
     CHD_LAUNCHED();
   }
   act_finalize_kernel<<<T, 256, 0, st>>>(*kd, N, C, w, mem_off, mem_idx, gdot, quad ? rowq : nullptr, gpart, nblk,
@@ -410,5 +431,5 @@ extern "C" int chd_activations(const chd_plan* plan, const chd_kernel_desc* kd, 
   if (!pl || !kd || !X || !cluster_of || !w0 || !alive || !yb || !ga || !act || T <= 0) return CHD_EINVAL;
   if (prune && !pruned) return CHD_EINVAL;
   return chd::act_launch(pl, kd, X, cluster_of, w0, alive, yb, ga, T, act, (size_t)pl->C, prune, pruned, 1, workspace,
-                         workspace_bytes, (cudaStream_t)stream);
+                         workspace_bytes, (cudaStream_t)stream, nullptr, 0);
 }

@@ -196,7 +196,7 @@ extern "C" size_t chd_workspace_bytes(const chd_plan* plan, int T) {
   gram_workspace(pl, T, -1, &gb);
   size_t b = regress_workspace(pl, T);
   b += align_up(T * n * ldk * sizeof(double), 256);  // K work matrices (prune chain)
-  b += align_up((size_t)T * pl->N, 256);             // active variable masks
+  b += 3 * align_up((size_t)T * pl->N, 256);         // active / previous / removed variable masks
   b += gb + act_workspace(pl, T);
   return b + 8192;
 }
@@ -237,7 +237,8 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
                                double* yb, uint32_t* keys, const double* gamma_grid, double* lambda_min,
                                double* gamma_min, int T, int first_step, int steps, int32_t* pruned, double* noise,
                                double* z_low, double* z_high, double* gamma, double* act, double* yb_chain,
-                               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+                               double* P_state, int* p_valid, int32_t* status, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   const Plan* pl = (const Plan*)plan;
   if (!pl || !kd || !X || !cluster_of || !w0 || !alive || !ga || !yb || !keys || !gamma_grid || !lambda_min ||
       !gamma_min || T <= 0 || steps < 0 || !pruned || !noise || !z_low || !z_high || !gamma || !act || !status)
@@ -250,6 +251,8 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
   bool ok = regress_carve(pl, T, cv, rb);
   double* K = cv.take<double>((size_t)T * n * ldk);
   uint8_t* w = cv.take<uint8_t>((size_t)T * N);
+  uint8_t* wprev = cv.take<uint8_t>((size_t)T * N);
+  uint8_t* wrem = cv.take<uint8_t>((size_t)T * N);
   size_t gb = 0;
   gram_workspace(pl, T, -1, &gb);
   char* gws = cv.take<char>(gb);
@@ -273,11 +276,27 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
       refresh_gamma_min_kernel<<<(T + 127) / 128, 128, 0, st>>>(lambda_min, gamma_min, T);
       CHD_LAUNCHED();
     }
+    // Gaussian mode with a caller-provided product-map cache: P holds prod_{d active}(1 + E_d) of the current
+    // mask; it is rebuilt from scratch when invalid and at the reference's own refresh cadence (every 50 steps),
+    // otherwise updated by one division per element after the prune.
+    const bool use_p = (kd->kind == CHD_KERNEL_GAUSSIAN) && P_state && p_valid;
+    if (use_p) {
+      if ((rc = active_vars_launch(w0, alive, cluster_of, N, C, T, wprev, st))) return rc;
+      if (!*p_valid || step % 50 == 0) {
+        if ((rc = gram_launch(pl, kd, X, X, n, wprev, T, nullptr, ldk, gws, gb, st, P_state, 1, nullptr))) return rc;
+        *p_valid = 1;
+      }
+    }
     if ((rc = act_launch(pl, kd, X, cluster_of, w0, alive, yb, ga, T, act + (size_t)s * C, (size_t)steps * C, 1,
-                         pruned + s, (size_t)steps, aws, ab, st)))
+                         pruned + s, (size_t)steps, aws, ab, st, use_p ? P_state : nullptr, ldk)))
       return rc;
     if ((rc = active_vars_launch(w0, alive, cluster_of, N, C, T, w, st))) return rc;
-    if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st))) return rc;
+    if (use_p) {
+      if ((rc = removed_vars_launch(wprev, w, T * N, wrem, st))) return rc;
+      if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st, P_state, 2, wrem))) return rc;
+    } else {
+      if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st, nullptr, 0, nullptr))) return rc;
+    }
     if ((rc = regress_core(pl, K, ldk, ga, T, gamma_grid, 0, 0.0, gamma_min, keys, keys, is_refresh(step + 1),
                            lambda_min, yb, (size_t)n, noise + s, z_low + s, z_high + s, gamma + s, (size_t)steps,
                            status, rb, st)))

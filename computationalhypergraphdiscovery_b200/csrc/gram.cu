@@ -52,7 +52,12 @@ constexpr int GS = GK + 4;    // smem row stride (== 4 mod 16 -> conflict-free D
 template <bool SYMM>
 __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ XcA, const double* __restrict__ XcB,
                                                    int nq, int n, int ldp, const int32_t* __restrict__ pcount,
-                                                   double* __restrict__ K, int ldk, chd_kernel_desc kd) {
+                                                   double* __restrict__ K, int ldk, chd_kernel_desc kd,
+                                                   double* __restrict__ P, int pmode,
+                                                   const double* __restrict__ Xr, const int32_t* __restrict__ rcount) {
+  // Gaussian product-map cache P = prod_{d active}(1 + E_d):
+  //   pmode 0: no cache;  1: compute the product and store it in P (K may be null: product only);
+  //   2: P <- P / prod_{d removed}(1 + E_d) with the removed variables gathered in Xr (n x ldp), no full product.
   __shared__ __align__(16) double As[GT * GS];
   __shared__ __align__(16) double Bs[GT * GS];
   const int t = blockIdx.y;
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
 #pragma unroll
         for (int b = 0; b < 2; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    if (gauss) {
+    if (gauss && pmode != 2) {
       const int dmax = min(GK, p - k0);
       for (int dd = 0; dd < dmax; ++dd) {
         double xr[4], xc[2][2];
@@ -142,6 +147,47 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
     __syncthreads();
   }
 
+  if (gauss && pmode == 2) {
+    // divisor F = prod over the removed variables (usually one), same tile staging as above
+    const int pr = rcount[t];
+    const double* R = Xr + (size_t)t * n * ldp;
+    for (int k0 = 0; k0 < pr; k0 += GK) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        int id = tid + s2 * 256;
+        int r = id >> 3, c2 = id & 7;
+        double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+        if (row0 + r < nq) va = *reinterpret_cast<const double2*>(R + (size_t)(row0 + r) * ldp + k0 + 2 * c2);
+        if (col0 + r < n) vb = *reinterpret_cast<const double2*>(R + (size_t)(col0 + r) * ldp + k0 + 2 * c2);
+        *reinterpret_cast<double2*>(&As[r * GS + 2 * c2]) = va;
+        *reinterpret_cast<double2*>(&Bs[r * GS + 2 * c2]) = vb;
+      }
+      __syncthreads();
+      const int dmax = min(GK, pr - k0);
+      for (int dd = 0; dd < dmax; ++dd) {
+        double xr[4], xc[2][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xr[a] = As[(wm * 32 + a * 8 + fr) * GS + dd];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          xc[b][0] = Bs[(wn * 16 + b * 8 + 2 * fk) * GS + dd];
+          xc[b][1] = Bs[(wn * 16 + b * 8 + 2 * fk + 1) * GS + dd];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              double df = xr[a] - xc[b][c];
+              prod[a][b][c] *= 1.0 + exp(-(df * df) * inv2l2);
+            }
+      }
+      __syncthreads();
+    }
+  }
+  double* Pt = P ? P + (size_t)t * nq * ldk : nullptr;
+
   // epilogue
   const double s = kd.scale, al = kd.alpha, qs = kd.quad_scale;
 #pragma unroll
@@ -163,11 +209,28 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
         } else {
           const double u = al + L;
           const double q = qs * (u * u) + (1.0 - al * al * qs);
-          r = (s * prod[a][b][c] + q) - 1.0;
+          double pv = prod[a][b][c];
+          if (pmode == 2) {
+            const bool in = (i < nq) && (j + c < n);
+            pv = in ? Pt[(size_t)i * ldk + j + c] / pv : 1.0;
+          }
+          prod[a][b][c] = pv;
+          r = (s * pv + q) - 1.0;
         }
         v[c] = r;
       }
-      if (i < nq) {
+      if (i < nq && Pt && gauss) {
+        if (j + 1 < n) {
+          *reinterpret_cast<double2*>(Pt + (size_t)i * ldk + j) = make_double2(prod[a][b][0], prod[a][b][1]);
+        } else if (j < n) {
+          Pt[(size_t)i * ldk + j] = prod[a][b][0];
+        }
+        if (SYMM && bi != bj) {
+          if (j < n) Pt[(size_t)j * ldk + i] = prod[a][b][0];
+          if (j + 1 < n) Pt[(size_t)(j + 1) * ldk + i] = prod[a][b][1];
+        }
+      }
+      if (i < nq && K) {
         if (j + 1 < n) {
           *reinterpret_cast<double2*>(Kt + (size_t)i * ldk + j) = make_double2(v[0], v[1]);
         } else if (j < n) {
@@ -202,14 +265,16 @@ int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes) {
   size_t b = 0;
   b += align_up((size_t)T * pl->N * sizeof(int32_t), 256);
   b += align_up((size_t)T * sizeof(int32_t), 256);
-  b += align_up((size_t)T * pl->n * ldp * sizeof(double), 256);
+  b += 2 * align_up((size_t)T * pl->n * ldp * sizeof(double), 256);   // Xc and the removed-variable gather
+  b += align_up((size_t)T * pl->N * sizeof(int32_t), 256) + align_up((size_t)T * sizeof(int32_t), 256);
   if (nq >= 0) b += align_up((size_t)T * nq * ldp * sizeof(double), 256);
   *bytes = b + 1024;
   return ldp;
 }
 
 int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
-                const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st) {
+                const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st,
+                double* P, int pmode, const uint8_t* wrem) {
   const int n = pl->n, N = pl->N;
   const bool symm = (Xq == X) && (nq == n);
   Carver cv(ws, ws_bytes);
@@ -217,7 +282,12 @@ int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, cons
   int32_t* idx = cv.take<int32_t>((size_t)T * N);
   int32_t* pc = cv.take<int32_t>(T);
   double* Xc = cv.take<double>((size_t)T * n * ldp);
+  double* Xr = cv.take<double>((size_t)T * n * ldp);
+  int32_t* idx2 = cv.take<int32_t>((size_t)T * N);
+  int32_t* pc2 = cv.take<int32_t>(T);
   double* Xqc = symm ? Xc : cv.take<double>((size_t)T * nq * ldp);
+  if (kd->kind != CHD_KERNEL_GAUSSIAN || !P) pmode = 0;
+  if (pmode == 2 && (!symm || !wrem)) return CHD_EINVAL;
   if (!cv.ok) {
     set_error("chd_gram: workspace too small (%zu needed, %zu given)", cv.off, ws_bytes);
     return CHD_ENOSPC;
@@ -238,12 +308,22 @@ int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, cons
       CHD_LAUNCHED();
     }
   }
+  if (pmode == 2) {
+    compact_kernel<<<T, 32, 0, st>>>(wrem, N, N, idx2, pc2);
+    CHD_LAUNCHED();
+    size_t total = (size_t)n * ldp;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    gather_kernel<<<dim3(blocks, T), 256, 0, st>>>(X, n, N, idx2, N, pc2, Xr, ldp);
+    CHD_LAUNCHED();
+  }
   if (symm) {
     const int tb = (n + GT - 1) / GT;
-    gram_kernel<true><<<dim3(tb * (tb + 1) / 2, T), 256, 0, st>>>(Xc, Xc, n, n, ldp, pc, K, ldk, *kd);
+    gram_kernel<true><<<dim3(tb * (tb + 1) / 2, T), 256, 0, st>>>(Xc, Xc, n, n, ldp, pc, K, ldk, *kd, P, pmode, Xr,
+                                                                 pc2);
   } else {
     const int ti = (nq + GT - 1) / GT, tj = (n + GT - 1) / GT;
-    gram_kernel<false><<<dim3(ti * tj, T), 256, 0, st>>>(Xqc, Xc, nq, n, ldp, pc, K, ldk, *kd);
+    gram_kernel<false><<<dim3(ti * tj, T), 256, 0, st>>>(Xqc, Xc, nq, n, ldp, pc, K, ldk, *kd, nullptr, 0, Xr, pc2);
   }
   CHD_LAUNCHED();
   return CHD_OK;
@@ -256,7 +336,8 @@ extern "C" int chd_gram(const chd_plan* plan, const chd_kernel_desc* kd, const d
                         void* stream) {
   const chd::Plan* pl = (const chd::Plan*)plan;
   if (!pl || !kd || !X || !Xq || !w || !K || T <= 0 || nq <= 0 || ldk < pl->n || (ldk & 1)) return CHD_EINVAL;
-  return chd::gram_launch(pl, kd, X, Xq, nq, w, T, K, ldk, workspace, workspace_bytes, (cudaStream_t)stream);
+  return chd::gram_launch(pl, kd, X, Xq, nq, w, T, K, ldk, workspace, workspace_bytes, (cudaStream_t)stream, nullptr,
+                          0, nullptr);
 }
 
 extern "C" int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, const double* X, const double* Xq,
@@ -272,7 +353,7 @@ extern "C" int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, cons
   size_t used = chd::align_up(cv.off, 256);
   // cross-Gram always takes the non-symmetric path: pass distinct pointer semantics via nq/Xq
   int rc = chd::gram_launch(pl, kd, X, Xq, nq, w, T, K, ldk, (char*)workspace + used, workspace_bytes - used,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr, 0, nullptr);
   if (rc) return rc;
   const int warps = 8;
   chd::predict_gemv_kernel<<<dim3((nq + warps - 1) / warps, T), warps * 32, 0, (cudaStream_t)stream>>>(

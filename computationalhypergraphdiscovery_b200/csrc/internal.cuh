@@ -23,12 +23,14 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
                  int T, cudaStream_t st);
 int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes);
 int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
-                const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st);
+                const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st,
+                double* P, int pmode, const uint8_t* wrem);
 size_t act_workspace(const Plan* pl, int T);
 int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const int32_t* cluster_of,
                const uint8_t* w0, uint8_t* alive, const double* yb, const double* ga, int T, double* act,
                size_t act_stride, int prune, int32_t* pruned, size_t pruned_stride, void* ws, size_t ws_bytes,
-               cudaStream_t st);
+               cudaStream_t st, const double* P, int ldk);
+int removed_vars_launch(const uint8_t* w_prev, const uint8_t* w_new, int count, uint8_t* wrem, cudaStream_t st);
 int profile_enable(int on);
 int profile_read(double* total_ms, int* launches);
 int active_vars_launch(const uint8_t* w0, const uint8_t* alive, const int32_t* cluster_of, int N, int C, int T,

@@ -121,13 +121,17 @@ int chd_activations(const chd_plan* plan, const chd_kernel_desc* kd, const doubl
  * lambda_min when step % 50 == 0 or p(p+1)/2 == N, p = N-step-1, _GraphDiscoveryMain.py:622-631);
  * gamma_min (T) carries the value between calls.
  * Chain outputs, [t][s] for s in [0, steps): pruned (int32), noise, z_low, z_high, gamma,
- * act (T x steps x C), yb_chain (T x steps x n, may be NULL). */
+ * act (T x steps x C), yb_chain (T x steps x n, may be NULL).
+ * P_state (T x n x ldk, may be NULL) + p_valid (HOST int, in/out): optional cache of the Gaussian product map
+ * prod_{d active}(1 + E_d) carried between calls; when given, a prune step costs one division per element instead
+ * of a full product (rebuilt when *p_valid == 0 and every 50 steps). */
 int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, const double* X, const int32_t* cluster_of,
                     const uint8_t* w0, uint8_t* alive, const double* ga, double* yb, uint32_t* keys,
                     const double* gamma_grid, double* lambda_min, double* gamma_min, int T, int first_step,
                     int steps, int32_t* pruned,
                     double* noise, double* z_low, double* z_high, double* gamma, double* act, double* yb_chain,
-                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                    double* P_state, int* p_valid, int32_t* status, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* predict (_GraphDiscoveryMain.py:934-979): out[t][q] = sum_j K(Xq, X, w[t])[q][j] * (-yb[t][j]). */
 int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
