@@ -313,9 +313,13 @@ def run_b200(args):
     value = total_steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (batched tridiagonalisation), timed with events around each launch
-    mats_per_launch = nkm * Tb * args.steps / max(tri_launches, 1)
+    # one tridiagonalisation = a few cooperative launches (multi-level restart x waves); all of them are bracketed
+    # by CUDA events inside the library.  achieved = credited flops of all matrices reduced in the timed region
+    # / summed duration of those launches.
+    n_mats = nkm * Tb * args.steps
+    mats_per_launch = n_mats / max(tri_launches, 1)
     dur = tri_ms * 1e-3 / max(tri_launches, 1)
-    achieved_tf = credited_flops_tridiag(n) * mats_per_launch / dur / 1e12
+    achieved_tf = credited_flops_tridiag(n) * n_mats / (tri_ms * 1e-3) / 1e12
     peak_tf = _native.dmma_peak_tflops(20000) if rank == 0 else 0.0
     peaks = {}
     try:
@@ -326,8 +330,8 @@ def run_b200(args):
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "tridiag_traffic.json")))
-        key = f"n{n}_mats{int(round(mats_per_launch))}"
-        traffic = tr.get(key)
+        per_matrix = tr.get(f"n{n}_per_matrix")
+        traffic = per_matrix * mats_per_launch if per_matrix else None
     except Exception:  # noqa: BLE001
         pass
     # bytes the one-stage reduction must stream: lower triangle of the trailing matrix once per column (symv,

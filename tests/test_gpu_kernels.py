@@ -89,13 +89,15 @@ def test_cross_gram_and_predict():
 
 
 @pytest.mark.parametrize("n,G,threads,bulk", [(97, 2, 0, 0), (200, 4, 0, 0), (310, 8, 0, 0), (256, 3, 0, 0),
-                                               (333, 5, 256, 1), (290, 4, 512, 0), (301, 6, 512, 1), (1100, 0, 0, 0)])
+                                               (333, 5, 256, 1), (290, 4, 512, 0), (301, 6, 512, 1), (1100, 0, 0, 0),
+                                               (1700, 0, 0, 0), (2300, 0, 0, 1)])
 def test_tridiag_matches_householder_model(n, G, threads, bulk, monkeypatch):
     """(threads, bulk) select the kernel variant: 256 threads x 2 CTAs/SM or 512 x 1, register or
     cp.async.bulk (UBLKCP) symv data path; 0 = the plan's default."""
     if threads:
         monkeypatch.setenv("CHD_TD_THREADS", str(threads))
     monkeypatch.setenv("CHD_TD_BULK", str(bulk))
+    monkeypatch.setenv("CHD_TD_LEVELS", "1" if n >= 1536 else "0")   # also exercise the multi-level restart
     nat = _native()
     N = 6
     X, _ = _data(n, N, 6)
