@@ -116,94 +116,52 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
   pl->n = n; pl->N = N; pl->C = C; pl->device = device;
   pl->sm_count = prop.multiProcessorCount;
   pl->smem_optin = prop.sharedMemPerBlockOptin;
-  pl->rows_per_chunk = 16;
-  pl->bulk = getenv("CHD_TD_BULK") ? atoi(getenv("CHD_TD_BULK")) : 0;
-  const char* force = getenv("CHD_TD_THREADS");
-  // Multi-level restart (CHD_TD_LEVELS=1): re-launch on the trailing sub-matrix with a layout tuned to its size.
-  // Measured on B200 it does not pay (n = 8192: 1165 ms vs 1006 ms per 4 matrices; neutral at 16 in flight):
-  // a sub-problem launch gives every matrix fewer resident threads than the tail of the big launch.  Off by
-  // default; kept (and tested) because the windowed kernel interface is what a two-stage reduction will reuse.
-  const int split_on = getenv("CHD_TD_LEVELS") ? atoi(getenv("CHD_TD_LEVELS")) : 0;
-  const size_t per_cta = (prop.sharedMemPerMultiprocessor - 2 * prop.reservedSharedMemPerBlock) / 2;
-  pl->smem_two = per_cta < pl->smem_optin ? per_cta : pl->smem_optin;
-
-  // CTA layout for a (sub-)problem of size m.  Preferred: 256-thread CTAs, two per SM (of different matrices),
-  // so one streams while the other sits in a barrier; large m does not leave room for two CTAs' shared memory:
-  // one 512-thread CTA per SM then.  G0 > 0 forces the CTAs per matrix.
-  auto tune = [&](int m, int G0, int nb, Level& L) -> bool {
-    int G = G0;
-    if (G <= 0) {
-      if (m <= 256) G = 2;
-      else if (m <= 640) G = 4;
-      else if (m <= 1536) G = 8;
-      else if (m <= 3072) G = 18;
-      else G = 37;
-    }
-    if (G > pl->sm_count) G = pl->sm_count;
-    int threads = 256;
-    bool ok = (force ? atoi(force) == 256 : m <= 6144) &&
-              tridiag_smem_bytes_for(m, G, 256, nb, pl->bulk) <= pl->smem_two;
-    if (!ok) {
-      threads = 512;
-      while (!(ok = tridiag_smem_bytes_for(m, G, 512, nb, pl->bulk) <= pl->smem_optin) && G < pl->sm_count) ++G;
-    }
-    if (!ok) return false;
-    const int slots = (threads == 256 ? 2 : 1) * pl->sm_count;
-    int wave = slots / G;
-    if (wave < 1) wave = 1;
-    if (G0 <= 0) {   // spread the CTA slots evenly over the matrices of a wave
-      const int Gfull = slots / wave;
-      if (Gfull > G && Gfull <= pl->sm_count) G = Gfull;
-    }
-    L.n_sub = m; L.G = G; L.threads = threads; L.wave = wave;
-    L.LR = tridiag_level_LR(m, G);
-    L.smem = tridiag_smem_bytes_for(m, G, threads, nb, pl->bulk);
-    return true;
-  };
-  // panel width: 32 if level 0 fits with it, else 16 (all levels share it: the back-transform walks one uniform
-  // panel partition)
-  Level L0;
   pl->nb = 32;
-  bool ok = tune(n, ctas_per_matrix, 32, L0) && L0.smem <= (L0.threads == 256 ? pl->smem_two : pl->smem_optin);
-  if (!ok) {
+  pl->rows_per_chunk = 16;
+  int G = ctas_per_matrix;
+  if (G <= 0) {
+    if (n <= 256) G = 2;
+    else if (n <= 640) G = 4;
+    else if (n <= 1536) G = 8;
+    else if (n <= 3072) G = 18;
+    else G = 37;
+  }
+  if (G > pl->sm_count) G = pl->sm_count;
+  pl->G = G;
+  // panel width 32 if the CTA's panel slice fits in shared memory, else 16, else more CTAs per matrix
+  // Preferred: 256-thread CTAs, two per SM (of different matrices), so one streams while the other sits in a
+  // barrier.  Large n does not leave room for two CTAs' shared memory: one 512-thread CTA per SM then.
+  const size_t per_cta = (prop.sharedMemPerMultiprocessor - 2 * prop.reservedSharedMemPerBlock) / 2;
+  auto fits = [&](size_t budget) {
+    pl->nb = 32;
+    if (tridiag_smem_bytes(pl) <= budget) return true;
     pl->nb = 16;
-    ok = tune(n, ctas_per_matrix, 16, L0);
+    return tridiag_smem_bytes(pl) <= budget;
+  };
+  const char* force = getenv("CHD_TD_THREADS");
+  pl->bulk = getenv("CHD_TD_BULK") ? atoi(getenv("CHD_TD_BULK")) : 0;
+  pl->threads = 256;
+  bool ok = (force ? atoi(force) == 256 : n <= 6144) && fits(per_cta < pl->smem_optin ? per_cta : pl->smem_optin);
+  if (!ok) {
+    pl->threads = 512;
+    if (ctas_per_matrix <= 0 && n > 4096) pl->G = 37;
+    while (!(ok = fits(pl->smem_optin)) && pl->G < pl->sm_count) pl->G += 1;
   }
   if (!ok) {
-    set_error("n=%d does not fit the tridiagonalisation's shared memory", n);
+    set_error("n=%d does not fit the tridiagonalisation's shared memory even with %d CTAs", n, pl->G);
     delete pl;
     return CHD_EINVAL;
   }
-  // levels: restart on the trailing sub-matrix when it has shrunk to about half (at a panel boundary)
-  pl->nlevels = 0;
-  int m = n, cn = -1;
-  while (true) {
-    Level L;
-    if (pl->nlevels == 0) L = L0;
-    else if (!tune(m, 0, pl->nb, L)) { set_error("level tuning failed for m=%d", m); delete pl; return CHD_EINVAL; }
-    L.cn = cn;
-    L.c_last = m - 2;
-    const bool can_split = split_on && ctas_per_matrix <= 0 && m >= 1536 && pl->nlevels < 10;
-    if (can_split) {
-      const int p = ((m + 1) / 2 + pl->nb - 1) / pl->nb;   // panels processed at this level
-      const int rest = m - p * pl->nb;
-      if (rest >= 512) {
-        L.c_last = p * pl->nb - 2;
-        pl->levels[pl->nlevels++] = L;
-        cn += p * pl->nb;
-        m = rest;
-        continue;
-      }
+  {
+    // spread the CTA slots evenly over the matrices of a wave
+    const int slots = (pl->threads == 256 ? 2 : 1) * pl->sm_count;
+    pl->wave = slots / pl->G;
+    if (pl->wave < 1) pl->wave = 1;
+    if (ctas_per_matrix <= 0) {
+      const int Gfull = slots / pl->wave;
+      if (Gfull > pl->G && Gfull <= pl->sm_count) pl->G = Gfull;
+      (void)fits(pl->threads == 256 ? (per_cta < pl->smem_optin ? per_cta : pl->smem_optin) : pl->smem_optin);
     }
-    pl->levels[pl->nlevels++] = L;
-    break;
-  }
-  pl->G = pl->levels[0].G; pl->threads = pl->levels[0].threads; pl->wave = pl->levels[0].wave;
-  pl->G_max = 0; pl->Gn_max = 0;
-  for (int i = 0; i < pl->nlevels; ++i) {
-    if (pl->levels[i].G > pl->G_max) pl->G_max = pl->levels[i].G;
-    const size_t gn = (size_t)pl->levels[i].G * pl->levels[i].n_sub;
-    if (gn > pl->Gn_max) pl->Gn_max = gn;
   }
   *plan = (chd_plan*)pl;
   return CHD_OK;

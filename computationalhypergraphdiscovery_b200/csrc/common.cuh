@@ -27,16 +27,6 @@ void set_error(const char* fmt, ...);
     CHD_CUDA(cudaGetLastError());               \
   } while (0)
 
-// One level of the tridiagonalisation: the reduction is restarted on the trailing sub-matrix whenever it has
-// shrunk to about half, with a CTA layout tuned to that size (fewer CTAs per matrix, more matrices in flight).
-struct Level {
-  int n_sub;     // size of the (sub-)problem
-  int cn;        // global index of its border column (-1: the target vector ga)
-  int c_last;    // last local column processed at this level (n_sub - 2 at the final level)
-  int G, threads, wave, LR;
-  size_t smem;
-};
-
 struct Plan {
   int n, N, C, device;
   int sm_count;
@@ -47,11 +37,6 @@ struct Plan {
   int bulk;       // symv data path: 1 = cp.async.bulk tile ring, 0 = register loads
   int rows_per_chunk;
   size_t smem_optin;
-  size_t smem_two;   // per-CTA budget when two CTAs share an SM
-  Level levels[12];
-  int nlevels;
-  int G_max;         // max CTAs per matrix over the levels
-  size_t Gn_max;     // max G * n_sub over the levels (column-part scratch per matrix)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

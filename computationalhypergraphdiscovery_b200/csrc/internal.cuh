@@ -10,8 +10,6 @@ struct TridiagBuffers {
 };
 
 size_t tridiag_smem_bytes(const Plan* pl);
-size_t tridiag_smem_bytes_for(int n, int G, int threads, int nb, int bulk);
-int tridiag_level_LR(int n, int G);
 size_t tridiag_workspace(const Plan* pl, int T);
 bool tridiag_carve(const Plan* pl, int T, Carver& cv, TridiagBuffers& tb);
 int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nbc,

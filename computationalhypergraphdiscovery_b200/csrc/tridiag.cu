@@ -50,10 +50,6 @@ struct TridiagArgs {
   unsigned* bar;  // T
   unsigned long long* timing;  // optional (debug): 8 accumulated phase times in ns, CTA 0 of matrix 0
   int n, G, nb, LR, nv;
-  // per-matrix strides (elements) and sub-problem window (multi-level restart)
-  size_t s_ga, s_B, s_de, s_beta0, s_v0, s_scr, s_vw, s_col, s_pg;
-  int ga_es;    // element stride of ga (1, or ldk when the border column is a column of A)
-  int c_last;   // last column processed by this launch (a panel end, or n - 2)
 };
 
 struct GroupBarrier {
@@ -138,23 +134,22 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
   constexpr int NW = TD_THREADS / 32;
 
   double* A = a.K + (size_t)m * a.strideK;
-  const double* ga = a.ga + (size_t)m * a.s_ga;
-  double* Bm = a.B ? a.B + (size_t)m * a.s_B : nullptr;
+  const double* ga = a.ga + (size_t)m * n;
+  double* Bm = a.B ? a.B + (size_t)m * n * a.ldb : nullptr;
   const int ldb = a.ldb, nbc = Bm ? a.nbc : 0;
-  double* dd = a.d + (size_t)m * a.s_de;
-  double* ee = a.e + (size_t)m * a.s_de;
-  double* tauv = a.tau + (size_t)m * a.s_de;
-  double* beta0p = a.beta0 + (size_t)m * a.s_beta0;
-  double* v0 = a.v0 + (size_t)m * a.s_v0;
-  double* ug = a.u + (size_t)m * a.s_scr;
-  double* rsum = a.rsum + (size_t)m * a.s_scr;
-  double* Vp = a.Vp + (size_t)m * a.s_vw;
-  double* Wp = a.Wp + (size_t)m * a.s_vw;
+  double* dd = a.d + (size_t)m * n;
+  double* ee = a.e + (size_t)m * n;
+  double* tauv = a.tau + (size_t)m * n;
+  double* v0 = a.v0 + (size_t)m * n;
+  double* ug = a.u + (size_t)m * n;
+  double* rsum = a.rsum + (size_t)m * n;
+  double* Vp = a.Vp + (size_t)m * nb * n;
+  double* Wp = a.Wp + (size_t)m * nb * n;
   double* part = a.part + (size_t)m * G * TD_PART;
   double* mypart = part + (size_t)g * TD_PART;
-  double* colpart = a.colpart + (size_t)m * a.s_col;
+  double* colpart = a.colpart + (size_t)m * G * n;
   double* mycol = colpart + (size_t)g * n;
-  double* pgram = a.pgram + (size_t)m * a.s_pg;
+  double* pgram = a.pgram + (size_t)m * n * nb;
 
   // ---- shared memory carve-up.  The reflector v is never cached whole: v_j = ug[j] * scale is recomputed
   // from the updated column in L2 where needed, which keeps the footprint small enough for two CTAs per SM.
@@ -194,7 +189,7 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
     for (int lr = tid; lr < LR; lr += TD_THREADS) {
       const int i = global_row(lr, g, G);
       if (i < n) {
-        const double x = ga[(size_t)i * a.ga_es];
+        const double x = ga[i];
         ug[i] = x;
         if (i > 0) ss += x * x;
       }
@@ -216,7 +211,7 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
   }
   if (timed) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tprev));
 
-  for (int c = -1; c <= a.c_last; ++c) {
+  for (int c = -1; c <= n - 2; ++c) {
     const int k = c - jj0;  // panel vectors already built
     const int R0 = c + 1;
 
@@ -243,7 +238,7 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
     {
       const double scale = sc[3];
       if (g == 0 && tid == 0) {
-        if (c < 0) beta0p[0] = sc[2]; else ee[c] = sc[2];
+        if (c < 0) a.beta0[m] = sc[2]; else ee[c] = sc[2];
         tauv[c + 1] = tau;
       }
       for (int i = R0 + tid; i < n; i += TD_THREADS) ycol[i] = 0.0;
@@ -632,7 +627,7 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
           }
         }
       }
-      const bool panel_end = (k + 1 == nb) || (c == n - 2) || (c == a.c_last);
+      const bool panel_end = (k + 1 == nb) || (c == n - 2);
       if (!panel_end) {
         // W_k at the pivot row of the next column (row R0), needed by every CTA
         if (wid == 1) {
@@ -745,7 +740,7 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
       TD_TICK(5)
       // ================= phase A for the next column cn = c + 1
       const int cn = c + 1;
-      if (cn <= n - 2 && c < a.c_last) {
+      if (cn <= n - 2) {
         const int kn = cn - jj0;
         const int R1 = cn + 1;
         double ss = 0.0;
@@ -776,12 +771,8 @@ __global__ void __launch_bounds__(TD_THREADS, 512 / TD_THREADS) tridiag_kernel(T
   if (timed)
     for (int q = 0; q < 8; ++q) a.timing[q] = tacc[q];
   if (g == 0 && tid == 0) {
-    if (a.c_last >= n - 2) {
-      dd[n - 1] = ldcg(A + (size_t)(n - 1) * ldk + (n - 1));
-      ee[n - 1] = 0.0;
-    } else {   // the next level continues with column c_last + 1 as its border column
-      dd[a.c_last + 1] = ldcg(A + (size_t)(a.c_last + 1) * ldk + (a.c_last + 1));
-    }
+    dd[n - 1] = ldcg(A + (size_t)(n - 1) * ldk + (n - 1));
+    ee[n - 1] = 0.0;
   }
 }
 
@@ -900,29 +891,23 @@ int profile_read(double* total_ms, int* launches) {
   return CHD_OK;
 }
 
-size_t tridiag_smem_bytes_for(int n, int G, int threads, int nb, int bulk) {
-  const int chunks = (n + TD_RB - 1) / TD_RB;
-  const int LR = (chunks + G - 1) / G * TD_RB;
-  const int stage = TD_KC * (threads / 4 + 8 + TD_SB);
-  const int ring = bulk ? TD_NS * TD_RB * threads : 0;   // TD_NS x 16 rows x (32 * warps) columns
-  size_t doubles = (size_t)(2 + threads / 32 + 2 * nb) * LR + 4 * TD_MAXNB + TD_BC + 512 + 40 + 8 + 8 +
+size_t tridiag_smem_bytes(const Plan* pl) {
+  const int chunks = (pl->n + TD_RB - 1) / TD_RB;
+  const int LR = (chunks + pl->G - 1) / pl->G * TD_RB;
+  const int stage = TD_KC * (pl->threads / 4 + 8 + TD_SB);
+  const int ring = pl->bulk ? TD_NS * TD_RB * pl->threads : 0;   // TD_NS x 16 rows x (32 * warps) columns
+  size_t doubles = (size_t)(2 + pl->threads / 32 + 2 * pl->nb) * LR + 4 * TD_MAXNB + TD_BC + 512 + 40 + 8 + 8 +
                    (size_t)max(stage, ring);
   return doubles * sizeof(double);
 }
-
-size_t tridiag_smem_bytes(const Plan* pl) {
-  return tridiag_smem_bytes_for(pl->n, pl->G, pl->threads, pl->nb, pl->bulk);
-}
-
-int tridiag_level_LR(int n, int G) { return ((n + TD_RB - 1) / TD_RB + G - 1) / G * TD_RB; }
 
 size_t tridiag_workspace(const Plan* pl, int T) {
   const size_t n = pl->n, nb = pl->nb;
   size_t b = 0;
   b += 4 * align_up(T * n * sizeof(double), 256);             // tau, v0, u, rsum
   b += 2 * align_up(T * nb * n * sizeof(double), 256);        // Vp, Wp
-  b += align_up((size_t)T * pl->Gn_max * sizeof(double), 256); // colpart
-  b += align_up((size_t)T * pl->G_max * TD_PART * sizeof(double), 256);
+  b += align_up((size_t)T * pl->G * n * sizeof(double), 256); // colpart
+  b += align_up((size_t)T * pl->G * TD_PART * sizeof(double), 256);
   b += align_up(T * n * nb * sizeof(double), 256);            // pgram
   b += align_up(T * sizeof(unsigned), 256);
   return b + 4096;
@@ -936,8 +921,8 @@ bool tridiag_carve(const Plan* pl, int T, Carver& cv, TridiagBuffers& tb) {
   tb.rsum = cv.take<double>(T * n);
   tb.Vp = cv.take<double>(T * nb * n);
   tb.Wp = cv.take<double>(T * nb * n);
-  tb.colpart = cv.take<double>((size_t)T * pl->Gn_max);
-  tb.part = cv.take<double>((size_t)T * pl->G_max * TD_PART);
+  tb.colpart = cv.take<double>((size_t)T * pl->G * n);
+  tb.part = cv.take<double>((size_t)T * pl->G * TD_PART);
   tb.pgram = cv.take<double>(T * n * nb);
   tb.bar = cv.take<unsigned>(T);
   return cv.ok;
@@ -945,11 +930,21 @@ bool tridiag_carve(const Plan* pl, int T, Carver& cv, TridiagBuffers& tb) {
 
 int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nbc,
                    double* d, double* e, double* beta0, const TridiagBuffers& tb, cudaStream_t st) {
-  const int n = pl->n, nb = pl->nb;
+  const int n = pl->n;
   if (nbc > TD_BC) return CHD_EINVAL;
+  const int chunks = (n + TD_RB - 1) / TD_RB;
+  TridiagArgs a;
+  a.K = K; a.strideK = (size_t)n * ldk; a.ldk = ldk; a.ga = ga; a.B = B; a.ldb = ldb; a.nbc = nbc;
+  a.d = d; a.e = e; a.beta0 = beta0; a.tau = tb.tau; a.v0 = tb.v0; a.u = tb.u; a.Vp = tb.Vp; a.Wp = tb.Wp;
+  a.rsum = tb.rsum; a.colpart = tb.colpart; a.part = tb.part; a.pgram = tb.pgram; a.bar = tb.bar;
+  a.n = n; a.G = pl->G; a.nb = pl->nb;
+  a.LR = (chunks + pl->G - 1) / pl->G * TD_RB;
+  a.nv = (int)align_up(n + 34, 2);
+  const size_t smem = tridiag_smem_bytes(pl);
   static unsigned long long* dbg = nullptr;
   static const bool dbg_on = getenv("CHD_TD_TIMING") != nullptr;
   if (dbg_on && !dbg) CHD_CUDA(cudaMalloc(&dbg, 8 * sizeof(unsigned long long)));
+  a.timing = dbg_on ? dbg : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     void* fns[4] = {(void*)tridiag_kernel<256, false>, (void*)tridiag_kernel<512, false>,
@@ -958,55 +953,42 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
       CHD_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
     attr_set = true;
   }
-  const size_t strideK = (size_t)n * ldk;
-  for (int lv = 0; lv < pl->nlevels; ++lv) {
-    const Level& L = pl->levels[lv];
-    const int cn = L.cn;          // global index of this level's border column
-    const size_t o = (size_t)(cn + 1);   // global index of the sub-matrix' first row / column
-    TridiagArgs a;
-    a.K = K + o * ldk + o; a.strideK = strideK; a.ldk = ldk;
-    if (lv == 0) { a.ga = ga; a.s_ga = (size_t)n; a.ga_es = 1; }
-    else { a.ga = K + o * ldk + cn; a.s_ga = strideK; a.ga_es = ldk; }
-    a.B = B ? B + o * ldb : nullptr; a.s_B = (size_t)n * ldb; a.ldb = ldb; a.nbc = nbc;
-    a.d = d + o; a.e = e + o; a.tau = tb.tau + o; a.s_de = (size_t)n;
-    if (lv == 0) { a.beta0 = beta0; a.s_beta0 = 1; a.v0 = tb.v0; a.s_v0 = (size_t)n; }
-    else { a.beta0 = e + cn; a.s_beta0 = (size_t)n; a.v0 = K + (size_t)cn * ldk + o; a.s_v0 = strideK; }
-    a.u = tb.u; a.rsum = tb.rsum; a.s_scr = (size_t)n;
-    a.Vp = tb.Vp; a.Wp = tb.Wp; a.s_vw = (size_t)nb * n;
-    a.colpart = tb.colpart; a.s_col = pl->Gn_max;
-    a.part = tb.part; a.pgram = tb.pgram + o * nb; a.s_pg = (size_t)n * nb; a.bar = tb.bar;
-    a.n = L.n_sub; a.G = L.G; a.nb = nb; a.LR = L.LR; a.nv = 0; a.c_last = L.c_last;
-    a.timing = (dbg_on && lv == 0) ? dbg : nullptr;
-    void* kfn = pl->bulk ? (L.threads == 256 ? (void*)tridiag_kernel<256, true> : (void*)tridiag_kernel<512, true>)
-                         : (L.threads == 256 ? (void*)tridiag_kernel<256, false> : (void*)tridiag_kernel<512, false>);
-    CHD_CUDA(cudaMemsetAsync(tb.bar, 0, sizeof(unsigned) * T, st));
-    for (int t0 = 0; t0 < T; t0 += L.wave) {
-      const int cnt = (T - t0 < L.wave) ? (T - t0) : L.wave;
-      TridiagArgs b = a;
-      b.K += (size_t)t0 * a.strideK; b.ga += (size_t)t0 * a.s_ga;
-      if (b.B) b.B += (size_t)t0 * a.s_B;
-      b.d += (size_t)t0 * a.s_de; b.e += (size_t)t0 * a.s_de; b.tau += (size_t)t0 * a.s_de;
-      b.beta0 += (size_t)t0 * a.s_beta0; b.v0 += (size_t)t0 * a.s_v0;
-      b.u += (size_t)t0 * a.s_scr; b.rsum += (size_t)t0 * a.s_scr;
-      b.Vp += (size_t)t0 * a.s_vw; b.Wp += (size_t)t0 * a.s_vw;
-      b.colpart += (size_t)t0 * a.s_col; b.part += (size_t)t0 * L.G * TD_PART;
-      b.pgram += (size_t)t0 * a.s_pg; b.bar += t0;
-      void* params[] = {&b};
-      if (g_prof_on) {
-        if (g_prof_used == g_prof_events.size()) {
-          cudaEvent_t e0, e1;
-          CHD_CUDA(cudaEventCreate(&e0));
-          CHD_CUDA(cudaEventCreate(&e1));
-          g_prof_events.emplace_back(e0, e1);
-        }
-        CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].first, st));
+  void* kfn = pl->bulk ? (pl->threads == 256 ? (void*)tridiag_kernel<256, true> : (void*)tridiag_kernel<512, true>)
+                       : (pl->threads == 256 ? (void*)tridiag_kernel<256, false> : (void*)tridiag_kernel<512, false>);
+  if (smem > pl->smem_optin) {
+    set_error("tridiag: %zu B shared memory needed, %zu available (raise ctas_per_matrix)", smem, pl->smem_optin);
+    return CHD_EINVAL;
+  }
+  CHD_CUDA(cudaMemsetAsync(tb.bar, 0, sizeof(unsigned) * T, st));
+  for (int t0 = 0; t0 < T; t0 += pl->wave) {
+    const int cnt = (T - t0 < pl->wave) ? (T - t0) : pl->wave;
+    TridiagArgs b = a;
+    b.K = K + (size_t)t0 * a.strideK;
+    b.ga = ga + (size_t)t0 * n;
+    b.B = B ? B + (size_t)t0 * n * ldb : nullptr;
+    b.d = d + (size_t)t0 * n; b.e = e + (size_t)t0 * n; b.beta0 = beta0 + t0;
+    b.tau = tb.tau + (size_t)t0 * n; b.v0 = tb.v0 + (size_t)t0 * n; b.u = tb.u + (size_t)t0 * n;
+    b.Vp = tb.Vp + (size_t)t0 * pl->nb * n; b.Wp = tb.Wp + (size_t)t0 * pl->nb * n;
+    b.rsum = tb.rsum + (size_t)t0 * n;
+    b.colpart = tb.colpart + (size_t)t0 * pl->G * n;
+    b.part = tb.part + (size_t)t0 * pl->G * TD_PART;
+    b.pgram = tb.pgram + (size_t)t0 * n * pl->nb;
+    b.bar = tb.bar + t0;
+    void* params[] = {&b};
+    if (g_prof_on) {
+      if (g_prof_used == g_prof_events.size()) {
+        cudaEvent_t e0, e1;
+        CHD_CUDA(cudaEventCreate(&e0));
+        CHD_CUDA(cudaEventCreate(&e1));
+        g_prof_events.emplace_back(e0, e1);
       }
-      CHD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(L.G, cnt), dim3(L.threads), params, L.smem, st));
-      g_launches.fetch_add(1);
-      if (g_prof_on) {
-        CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].second, st));
-        ++g_prof_used;
-      }
+      CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].first, st));
+    }
+    CHD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(pl->G, cnt), dim3(pl->threads), params, smem, st));
+    g_launches.fetch_add(1);
+    if (g_prof_on) {
+      CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].second, st));
+      ++g_prof_used;
     }
   }
   if (dbg_on) {
