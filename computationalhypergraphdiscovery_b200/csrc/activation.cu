@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(256) gmat_kernel(const double* __restrict__ X,
     const int d = d0 + ty * 4 + r, e = e0 + tx;
     if (d < N && e < N) {
       G[(size_t)d * N + e] = acc[r];
-      G[(size_t)e * N + d] = acc[r];
+      // mirror only off-diagonal tiles: inside a diagonal tile (d, e) and (e, d) are both computed (with different
+      // rounding), and a mirrored store would race with the other thread's own store
+      if (d0 != e0) G[(size_t)e * N + d] = acc[r];
     }
   }
 }
