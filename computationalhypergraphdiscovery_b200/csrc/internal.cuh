@@ -21,6 +21,11 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
                  double* gamma_min, int want_lambda_min, double* lambda_min, double* eta, double* uu, double* x,
                  double* noise, double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status,
                  int T, cudaStream_t st);
+int gamma_band_launch(const Plan* pl, int B, const double* band, const double* gt, const double* grid, double* loss,
+                      double* Bq, int ldb, int nz, int gamma_min_mode, double gamma_min_base, double* gamma_min,
+                      int want_lambda_min, double* lambda_min, double* Dg, double* Ug, double* x, double* noise,
+                      double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status, int T,
+                      cudaStream_t st);
 int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes);
 int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
                 const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st,
