@@ -1,0 +1,80 @@
+"""CPU proof that the two-stage formulation (tests/twostage_model.py: dense -> band by block reflectors, band ->
+tridiagonal by bulge chasing for the loss, banded Cholesky solves for everything that needs vectors) equals the
+eigendecomposition formulation of the reference (interpolatory.py:24-135, restated in oracle/regression.py)."""
+import numpy as np
+import pytest
+
+from oracle import kernels, regression, jaxprng
+import tridiag_model as tm
+import twostage_model as ts
+
+
+@pytest.fixture(scope="module")
+def problem():
+    rng = np.random.default_rng(1)
+    n, N = 150, 6
+    X = rng.standard_normal((n, N))
+    X[:, 0] = X[:, 1] * X[:, 2] + 0.1 * rng.standard_normal(n)
+    X = (X - X.mean(0)) / X.std(0)
+    specs = kernels.make_specs([("linear", 2.0, None), ("quadratic", 1.0, None), ("gaussian", 1.0, 1.0)])
+    w = np.ones(N)
+    w[0] = 0
+    return X, X[:, 0].copy(), specs, w
+
+
+@pytest.mark.parametrize("b", [4, 8, 32])
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_twostage_equals_eigen_formulation(problem, k, b):
+    X, ga, specs, w = problem
+    n = X.shape[0]
+    K = kernels.gram(specs[k], X, X, w)
+    lam, V = np.linalg.eigh(K)
+    P = V.T @ ga
+    lg = regression.make_loss(lam, P)
+    key = jaxprng.PRNGKey(3)
+    S = jaxprng.normal(key, (n, 100))
+    s1 = ts.stage1(K, ga, b, S)
+    scale = abs(lam).max()
+    assert s1["resid"] < 1e-12 * scale
+    assert abs(s1["beta0"] ** 2 - ga @ ga) < 1e-12 * (ga @ ga)
+    Tb = ts.band_to_dense(s1["band"])
+    assert np.abs(np.linalg.eigvalsh(Tb) - lam).max() < 1e-13 * scale * n
+    d, e = ts.stage2(s1["band"])
+    Tt = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    assert np.abs(np.linalg.eigvalsh(Tt) - lam).max() < 1e-13 * scale * n
+    for g in (0.1, 5.0, 2e3):
+        f, fp = lg(g)
+        f2, fp2 = tm.loss_and_grad(d, e, g)
+        assert abs(f - f2) < 1e-10 * abs(f)
+        assert abs(fp - fp2) < 1e-7 * max(abs(fp), 1e-6)
+    g = 0.05
+    yb, noise = regression.solve_variationnal(ga, g, lam, V)
+    L = ts.band_cholesky(s1["band"], g)
+    e0 = np.zeros(n)
+    e0[0] = 1.0
+    _, x = ts.band_solve(L, e0)
+    yb2 = -s1["beta0"] * ts.apply_Q(s1, x)
+    assert np.linalg.norm(yb - yb2) < 1e-9 * np.linalg.norm(yb)
+    assert abs(g * (x @ x) / x[0] - noise) < 1e-9 * noise
+    zl, zh = regression.Z_test(g, lam, V, key)
+    Y, Z = ts.band_solve(L, s1["Bq"])
+    nz = np.sort(g * np.sum(Z * Z, 0) / np.sum(Y * Y, 0))
+    assert abs(nz[5] - zl) < 1e-9 * zl and abs(nz[95] - zh) < 1e-9 * zh
+
+
+@pytest.mark.parametrize("n,b", [(33, 32), (34, 32), (65, 32), (70, 8), (9, 4), (5, 4), (3, 4)])
+def test_twostage_ragged_sizes(n, b):
+    rng = np.random.default_rng(n)
+    F = rng.standard_normal((n, n + 3))
+    K = F @ F.T / n
+    ga = rng.standard_normal(n)
+    lam = np.linalg.eigvalsh(K)
+    s1 = ts.stage1(K, ga, b)
+    assert s1["resid"] < 1e-12 * lam.max()
+    d, e = ts.stage2(s1["band"])
+    Tt = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    assert np.abs(np.linalg.eigvalsh(Tt) - lam).max() < 1e-12 * lam.max()
+    g = 0.3
+    F1 = ga @ np.linalg.solve(K + g * np.eye(n), ga)
+    eta, _, _ = tm.eta_jets(d, np.r_[e, 0.0], g)
+    assert abs(s1["beta0"] ** 2 / eta - F1) < 1e-11 * abs(F1)

@@ -1,0 +1,191 @@
+"""NumPy model of the two-stage reduction the CUDA path implements.  Test helper: proves on
+the CPU that the two-stage formulation equals the reference's eigendecomposition formulation
+(interpolatory.py:24-135) and serves as the checker for the CUDA kernels of csrc/band.cu, chase.cu, bandsolve.cu.
+
+  stage 0   H_{-1} ga = beta0 e_0,  K1 = H_{-1} K H_{-1}
+  stage 1   K1 -> symmetric band T_b of half-width b: per panel k (columns c0 = k b .. c0+b-1) a Householder QR of
+            the block below the band, Q_k = I - V T V^T (compact WY), and the two-sided rank-2b update
+            A22 -= V W^T + W V^T,  W = (Y - 1/2 V T^T (V^T Y)) T,  Y = A22 V         -- all GEMM-shaped
+  stage 2   T_b -> tridiagonal T (values only) by Householder bulge chasing; row/column 0 is never touched, so
+            e_0 is preserved and  beta0^2 e_0^T (T+g)^-1 e_0 = ga^T (K+g)^-1 ga  (the loss only needs d, e)
+  solve     everything that needs vectors (x, the Z-test) is solved in band coordinates with a banded Cholesky of
+            T_b + g I: the stage-2 transformations are never applied to a vector.
+"""
+import numpy as np
+
+
+def reflector(u):
+    """LAPACK dlarfg: returns v (v[0] = 1), tau, beta with (I - tau v v^T) u = beta e_0."""
+    alpha = u[0]
+    xnorm = np.linalg.norm(u[1:]) if u.size > 1 else 0.0
+    if xnorm == 0.0:
+        v = np.zeros(u.size)
+        v[0] = 1.0
+        return v, 0.0, alpha
+    beta = -np.copysign(np.hypot(alpha, xnorm), alpha)
+    tau = (beta - alpha) / beta
+    v = u / (alpha - beta)
+    v[0] = 1.0
+    return v, tau, beta
+
+
+def panel_qr(P):
+    """Unblocked Householder QR of an m x b block (m >= 1).  Returns R-over-zeros (m x b), V (m x b unit lower
+    trapezoidal, zero columns where no reflector exists), tau (b) and the compact-WY factor T (b x b upper)."""
+    m, b = P.shape
+    P = P.copy()
+    V = np.zeros((m, b))
+    tau = np.zeros(b)
+    for t in range(min(b, m - 1)):
+        v, tau[t], beta = reflector(P[t:, t].copy())
+        V[t:, t] = v
+        P[t, t] = beta
+        P[t + 1:, t] = 0.0
+        if t + 1 < b:
+            w = tau[t] * (v @ P[t:, t + 1:])
+            P[t:, t + 1:] -= np.outer(v, w)
+    G = V.T @ V
+    T = np.zeros((b, b))
+    for t in range(b):
+        T[t, t] = tau[t]
+        if t:
+            T[:t, t] = -tau[t] * (T[:t, :t] @ G[:t, t])
+    return P, V, tau, T
+
+
+def stage1(K, ga, b, S=None):
+    """Returns dict(band (n x (b+1)): band[i, t] = T_b[i, i-t]; beta0; panels: list of (r0, V, T); v0, tau0;
+    Bq = Q^T S)."""
+    n = K.shape[0]
+    A = K.copy()
+    Bq = None if S is None else S.copy()
+    v0, tau0, beta0 = reflector(ga.copy())
+    w = tau0 * (A @ v0)
+    w += (-0.5 * tau0 * (w @ v0)) * v0
+    A -= np.outer(v0, w) + np.outer(w, v0)
+    if Bq is not None:
+        Bq -= tau0 * np.outer(v0, v0 @ Bq)
+    panels = []
+    k = 0
+    while True:
+        c0 = k * b
+        r0 = c0 + b
+        if n - r0 < 2:
+            break
+        R, V, tau, T = panel_qr(A[r0:, c0:r0])
+        A[r0:, c0:r0] = R
+        A[c0:r0, r0:] = R.T
+        A22 = A[r0:, r0:]
+        Y = A22 @ V
+        M = V.T @ Y
+        W = (Y - 0.5 * V @ (T.T @ M)) @ T
+        A22 -= V @ W.T + W @ V.T
+        if Bq is not None:
+            Bq[r0:] -= V @ (T.T @ (V.T @ Bq[r0:]))
+        panels.append((r0, V, T))
+        k += 1
+    band = np.zeros((n, b + 1))
+    for t in range(min(b + 1, n)):
+        band[t:, t] = np.diagonal(A, -t)
+    resid = np.abs(np.tril(A, -(b + 1))).max() if n > b + 1 else 0.0
+    return dict(band=band, beta0=beta0, panels=panels, v0=v0, tau0=tau0, Bq=Bq, resid=resid)
+
+
+def apply_Q(s1, x):
+    """Q x with Q = H_{-1} Q_0 Q_1 ... (the back-transformation yb = -beta0 Q x_b)."""
+    x = np.array(x, dtype=np.float64, copy=True)
+    for (r0, V, T) in reversed(s1["panels"]):
+        x[r0:] -= V @ (T @ (V.T @ x[r0:]))
+    x -= s1["tau0"] * s1["v0"] * (s1["v0"] @ x)
+    return x
+
+
+def band_to_dense(band):
+    n, b1 = band.shape
+    A = np.zeros((n, n))
+    for t in range(min(b1, n)):
+        A += np.diag(band[t:, t], -t)
+        if t:
+            A += np.diag(band[t:, t], t)
+    return A
+
+
+def stage2(band):
+    """Band -> tridiagonal by Householder bulge chasing (Murata-Horikoshi / Lang), values only.
+    Sweep j annihilates column j below the sub-diagonal with a reflector on rows j+1..j+b; the fill-in
+    (one b x b bulge per hop) is chased down the band: each hop h applies the incoming reflector two-sided to
+    the diagonal block I_h, from the right to the block below it, and generates the next reflector from that
+    block's first column.  Returns d (n), e (n-1)."""
+    n, b1 = band.shape
+    b = b1 - 1
+    A = band_to_dense(band)
+    if b > 1:
+        for j in range(n - 2):
+            lo = j + 1
+            hi = min(j + b, n - 1)            # inclusive
+            if hi <= lo:
+                break
+            v, tau, beta = reflector(A[lo:hi + 1, j].copy())
+            A[lo:hi + 1, j] = 0.0
+            A[lo, j] = beta
+            A[j, lo:hi + 1] = A[lo:hi + 1, j]
+            while True:
+                I = slice(lo, hi + 1)
+                D = A[I, I]
+                p = tau * (D @ v)
+                p += (-0.5 * tau * (p @ v)) * v
+                D -= np.outer(v, p) + np.outer(p, v)
+                lo2 = hi + 1
+                hi2 = min(hi + b, n - 1)
+                if lo2 > n - 1:
+                    break
+                I2 = slice(lo2, hi2 + 1)
+                Sb = A[I2, I]
+                Sb -= tau * np.outer(Sb @ v, v)
+                if hi2 > lo2:
+                    v2, tau2, beta2 = reflector(Sb[:, 0].copy())
+                    Sb[:, 0] = 0.0
+                    Sb[0, 0] = beta2
+                    Sb[:, 1:] -= tau2 * np.outer(v2, v2 @ Sb[:, 1:])
+                else:
+                    v2, tau2 = np.ones(1), 0.0
+                A[I, I2] = Sb.T
+                if hi2 <= lo2:
+                    break
+                v, tau, lo, hi = v2, tau2, lo2, hi2
+    return np.diagonal(A).copy(), np.diagonal(A, -1).copy()
+
+
+def band_cholesky(band, g):
+    """Lower banded Cholesky T_b + g I = L L^T; L[i, t] = L(i, i-t)."""
+    n, b1 = band.shape
+    b = b1 - 1
+    L = np.zeros((n, b1))
+    for i in range(n):
+        for t in range(min(b, i), -1, -1):          # column j = i - t, ascending j
+            j = i - t
+            s = band[i, t] + (g if t == 0 else 0.0)
+            for p in range(1, b + 1):               # common columns j - p
+                if j - p < 0 or t + p > b:
+                    break
+                s -= L[i, t + p] * L[j, p]
+            L[i, t] = np.sqrt(s) if t == 0 else s / L[j, 0]
+    return L
+
+
+def band_solve(L, R):
+    """Returns (y, z): y = L^-1 R, z = L^-T y  (R: (n,) or (n, m))."""
+    n, b1 = L.shape
+    b = b1 - 1
+    y = np.array(R, dtype=np.float64, copy=True)
+    for i in range(n):
+        for p in range(1, min(b, i) + 1):
+            y[i] = y[i] - L[i, p] * y[i - p]
+        y[i] = y[i] / L[i, 0]
+    z = y.copy()
+    for i in range(n - 1, -1, -1):
+        for p in range(1, b + 1):
+            if i + p < n:
+                z[i] = z[i] - L[i + p, p] * z[i + p]
+        z[i] = z[i] / L[i, 0]
+    return y, z
