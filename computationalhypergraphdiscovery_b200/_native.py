@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libchd_b200.so")
 KERNEL_LINEAR, KERNEL_QUADRATIC, KERNEL_GAUSSIAN = 0, 1, 2
 Z_SAMPLES = 100
 GRID_POINTS = 10000
+BAND, BAND_LD = 32, 34
 ST_BFGS_SUCCESS, ST_USED_MEDIAN, ST_GRID_EDGE = 1, 2, 4
 
 
@@ -54,6 +55,12 @@ _SIGNATURES = {
     "chd_dmma_peak": (_i, [_i, ctypes.POINTER(_d)]),
     "chd_gamma_band": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _sz, _vp]),
+    "chd_band_workspace_bytes": (_sz, [_vp, _i]),
+    "chd_band_reduce": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "chd_band_backtransform": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "chd_band_chase": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "chd_band_solve": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "chd_plan_set_two_stage": (_i, [_vp, _i]),
     "chd_profile_enable": (_i, [_i]),
     "chd_profile_read": (_i, [ctypes.POINTER(_d), ctypes.POINTER(_i)]),
 }
@@ -210,6 +217,59 @@ class Plan:
                                      _ptr(out["z_low"]), _ptr(out["z_high"]), _ptr(out["gamma"]),
                                      _ptr(out["lambda_min"]), _ptr(out["status"]), _ptr(ws), ws.numel(), _stream()),
                "chd_gamma_band")
+        return out
+
+    # ---- two-stage building blocks
+    def set_two_stage(self, on):
+        _check(load().chd_plan_set_two_stage(self._h, int(bool(on))), "chd_plan_set_two_stage")
+        self._ws = None
+
+    def band_workspace(self, T):
+        need = int(load().chd_band_workspace_bytes(self._h, int(T)))
+        if getattr(self, "_bws", None) is None or self._bws.numel() < need:
+            self._bws = None
+            self._bws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._bws
+
+    def band_reduce(self, K, ga, B=None):
+        """K (T, n, ldk) destroyed (holds the block reflectors afterwards); returns band (T, n, BAND_LD), beta0 (T).
+        B (T, n, nz) is replaced by Q^T B."""
+        T = K.shape[0]
+        band = torch.empty((T, self.n, BAND_LD), dtype=torch.float64, device=self.device)
+        beta0 = torch.empty(T, dtype=torch.float64, device=self.device)
+        ws = self.band_workspace(T)
+        ldb = B.shape[2] if B is not None else 0
+        _check(load().chd_band_reduce(self._h, _ptr(K), self.ldk, _ptr(ga), T, _ptr(B), ldb, ldb, _ptr(band),
+                                      _ptr(beta0), _ptr(ws), ws.numel(), _stream()), "chd_band_reduce")
+        return band, beta0
+
+    def band_backtransform(self, K, x, beta0):
+        T = K.shape[0]
+        out = torch.empty((T, self.n), dtype=torch.float64, device=self.device)
+        ws = self.band_workspace(T)
+        _check(load().chd_band_backtransform(self._h, _ptr(K), self.ldk, _ptr(x), _ptr(beta0), _ptr(out), T, _ptr(ws),
+                                             ws.numel(), _stream()), "chd_band_backtransform")
+        return out
+
+    def band_chase(self, band):
+        T = band.shape[0]
+        d = torch.empty((T, self.n), dtype=torch.float64, device=self.device)
+        e = torch.empty((T, self.n), dtype=torch.float64, device=self.device)
+        ws = self.band_workspace(T)
+        _check(load().chd_band_chase(self._h, _ptr(band), T, _ptr(d), _ptr(e), _ptr(ws), ws.numel(), _stream()),
+               "chd_band_chase")
+        return d, e
+
+    def band_solve(self, band, gamma_used, Bq=None):
+        T = band.shape[0]
+        dev, f64 = self.device, torch.float64
+        out = dict(x=torch.empty((T, self.n), dtype=f64, device=dev), noise=torch.empty(T, dtype=f64, device=dev),
+                   z_low=torch.empty(T, dtype=f64, device=dev), z_high=torch.empty(T, dtype=f64, device=dev))
+        ws = self.band_workspace(T)
+        nz = Bq.shape[2] if Bq is not None else 0
+        _check(load().chd_band_solve(self._h, _ptr(band), _ptr(gamma_used), _ptr(Bq), nz, nz, T, _ptr(out["x"]),
+                                     _ptr(out["noise"]), _ptr(out["z_low"]), _ptr(out["z_high"]), _ptr(ws),
+                                     ws.numel(), _stream()), "chd_band_solve")
         return out
 
     def tridiag(self, K, ga, B=None):

@@ -28,6 +28,10 @@ struct RegressBuffers {
   uint32_t* subkeys;
   double *B, *d, *e, *beta0, *loss, *eta, *uu, *x;
   TridiagBuffers tb;
+  // two-stage path
+  BandBuffers bb;
+  int* prog;
+  double *Lg, *gu;
 };
 
 static size_t regress_workspace(const Plan* pl, int T) {
@@ -38,6 +42,11 @@ static size_t regress_workspace(const Plan* pl, int T) {
   b += 5 * align_up(T * n * sizeof(double), 256);
   b += align_up(T * sizeof(double), 256);
   b += align_up((size_t)T * CHD_GRID_POINTS * sizeof(double), 256);
+  if (pl->two_stage) {
+    b += band_workspace(pl, T) + chase_workspace(pl, T);
+    b += align_up((size_t)T * n * CHD_BAND_LD * sizeof(double), 256) + align_up(T * sizeof(double), 256);
+    return b + 4096;
+  }
   return b + tridiag_workspace(pl, T) + 4096;
 }
 
@@ -52,6 +61,13 @@ static bool regress_carve(const Plan* pl, int T, Carver& cv, RegressBuffers& rb)
   rb.x = cv.take<double>(T * n);
   rb.beta0 = cv.take<double>(T);
   rb.loss = cv.take<double>((size_t)T * CHD_GRID_POINTS);
+  if (pl->two_stage) {
+    const bool ok = band_carve(pl, T, cv, rb.bb);
+    rb.prog = cv.take<int>((size_t)T * n + 64);
+    rb.Lg = cv.take<double>((size_t)T * n * CHD_BAND_LD);
+    rb.gu = cv.take<double>(T);
+    return ok && cv.ok;
+  }
   return tridiag_carve(pl, T, cv, rb.tb) && cv.ok;
 }
 
@@ -64,6 +80,20 @@ static int regress_core(const Plan* pl, double* K, int ldk, const double* ga, in
   int rc;
   if ((rc = chd_split(keys, T, keys_out, rb.subkeys, st))) return rc;
   if ((rc = chd_normal(rb.subkeys, T, pl->n, CHD_Z_SAMPLES, rb.B, ZLD, st))) return rc;
+  if (pl->two_stage) {
+    // dense -> band (DMMA GEMMs) -> tridiagonal (values only); gamma search on (d, e); solve + Z-test in band
+    // coordinates; yb = -beta0 Q x through the block reflectors
+    if ((rc = band_reduce_launch(pl, K, ldk, ga, T, rb.B, ZLD, CHD_Z_SAMPLES, rb.beta0, rb.bb, st))) return rc;
+    if ((rc = chase_launch(pl, rb.bb.bandW, rb.prog, rb.d, rb.e, T, st))) return rc;
+    if ((rc = gamma_launch(pl, rb.d, rb.e, rb.beta0, grid, rb.loss, nullptr, ZLD, 0, gamma_min_mode, gamma_min_base,
+                           gamma_min, want_lambda_min, lambda_min, rb.eta, rb.uu, rb.x, noise, z_low, z_high, gamma,
+                           out_stride, status, T, st, rb.gu)))
+      return rc;
+    if ((rc = band_solve_launch(pl, rb.bb.bandS, rb.Lg, rb.gu, rb.B, ZLD, CHD_Z_SAMPLES, rb.x, noise, z_low, z_high,
+                                out_stride, T, st)))
+      return rc;
+    return backtransform2_launch(pl, K, ldk, rb.bb, rb.x, rb.beta0, yb, yb_stride, T, st);
+  }
   if ((rc = tridiag_launch(pl, K, ldk, ga, T, rb.B, ZLD, CHD_Z_SAMPLES, rb.d, rb.e, rb.beta0, rb.tb, st))) return rc;
   if ((rc = gamma_launch(pl, rb.d, rb.e, rb.beta0, grid, rb.loss, rb.B, ZLD, CHD_Z_SAMPLES, gamma_min_mode,
                          gamma_min_base, gamma_min, want_lambda_min, lambda_min, rb.eta, rb.uu, rb.x, noise, z_low,
@@ -118,6 +148,7 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
   pl->smem_optin = prop.sharedMemPerBlockOptin;
   pl->nb = 32;
   pl->rows_per_chunk = 16;
+  pl->two_stage = getenv("CHD_TWO_STAGE") ? atoi(getenv("CHD_TWO_STAGE")) : 0;
   int G = ctas_per_matrix;
   if (G <= 0) {
     if (n <= 256) G = 2;
@@ -326,6 +357,84 @@ extern "C" int chd_gamma_band(const chd_plan* plan, int B, const double* band, c
   return gamma_band_launch(pl, B, band, gt, gamma_grid, loss, Bq, ldb, Bq ? nz : 0, gamma_min_mode, gamma_min_base,
                            gamma_min, lambda_min != nullptr, lambda_min, Dg, Ug, x, noise, z_low, z_high, gamma, 1,
                            status, T, (cudaStream_t)stream);
+}
+
+// ---- two-stage building blocks (inspection / test entry points)
+struct BandWs {
+  BandBuffers bb;
+  int* prog;
+  double *Lg, *dd, *ee;
+};
+static bool band_ws_carve(const Plan* pl, int T, void* ws, size_t bytes, BandWs& w) {
+  Carver cv(ws, bytes);
+  const bool ok = band_carve(pl, T, cv, w.bb);
+  w.prog = cv.take<int>((size_t)T * pl->n + 64);
+  w.Lg = cv.take<double>((size_t)T * pl->n * CHD_BAND_LD);
+  return ok && cv.ok;
+}
+
+extern "C" size_t chd_band_workspace_bytes(const chd_plan* plan, int T) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || T <= 0) return 0;
+  return band_workspace(pl, T) + chase_workspace(pl, T) +
+         align_up((size_t)T * pl->n * CHD_BAND_LD * sizeof(double), 256) + 8192;
+}
+
+extern "C" int chd_band_reduce(const chd_plan* plan, double* K, int ldk, const double* ga, int T, double* B, int ldb,
+                               int nb_cols, double* band, double* beta0, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !K || !ga || !band || !beta0 || T <= 0 || ldk < pl->n || (ldk & 1)) return CHD_EINVAL;
+  BandWs w;
+  if (!band_ws_carve(pl, T, workspace, workspace_bytes, w)) return CHD_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = band_reduce_launch(pl, K, ldk, ga, T, B, ldb, B ? nb_cols : 0, beta0, w.bb, st);
+  if (rc) return rc;
+  CHD_CUDA(cudaMemcpyAsync(band, w.bb.bandS, (size_t)T * pl->n * CHD_BAND_LD * sizeof(double),
+                           cudaMemcpyDeviceToDevice, st));
+  return CHD_OK;
+}
+
+extern "C" int chd_band_backtransform(const chd_plan* plan, const double* K, int ldk, const double* x,
+                                      const double* beta0, double* out, int T, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !K || !x || !beta0 || !out || T <= 0) return CHD_EINVAL;
+  BandWs w;
+  if (!band_ws_carve(pl, T, workspace, workspace_bytes, w)) return CHD_ENOSPC;
+  return backtransform2_launch(pl, K, ldk, w.bb, x, beta0, out, (size_t)pl->n, T, (cudaStream_t)stream);
+}
+
+extern "C" int chd_band_chase(const chd_plan* plan, const double* band, int T, double* d, double* e, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !band || !d || !e || T <= 0) return CHD_EINVAL;
+  BandWs w;
+  if (!band_ws_carve(pl, T, workspace, workspace_bytes, w)) return CHD_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = pl->n;
+  CHD_CUDA(cudaMemsetAsync(w.bb.bandW, 0, (size_t)T * n * CHD_CHASE_LD * sizeof(double), st));
+  CHD_CUDA(cudaMemcpy2DAsync(w.bb.bandW, CHD_CHASE_LD * sizeof(double), band, CHD_BAND_LD * sizeof(double),
+                             (CHD_BAND + 1) * sizeof(double), (size_t)T * n, cudaMemcpyDeviceToDevice, st));
+  return chase_launch(pl, w.bb.bandW, w.prog, d, e, T, st);
+}
+
+extern "C" int chd_band_solve(const chd_plan* plan, const double* band, const double* gamma_used, double* Bq, int ldb,
+                              int nz, int T, double* x, double* noise, double* z_low, double* z_high, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  const Plan* pl = (const Plan*)plan;
+  if (!pl || !band || !gamma_used || !x || !noise || !z_low || !z_high || T <= 0) return CHD_EINVAL;
+  BandWs w;
+  if (!band_ws_carve(pl, T, workspace, workspace_bytes, w)) return CHD_ENOSPC;
+  return band_solve_launch(pl, band, w.Lg, gamma_used, Bq, ldb, nz, x, noise, z_low, z_high, 1, T,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int chd_plan_set_two_stage(chd_plan* plan, int on) {
+  Plan* pl = (Plan*)plan;
+  if (!pl) return CHD_EINVAL;
+  pl->two_stage = on ? 1 : 0;
+  return CHD_OK;
 }
 
 extern "C" int chd_profile_enable(int on) { return profile_enable(on); }

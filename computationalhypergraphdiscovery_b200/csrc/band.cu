@@ -1,0 +1,974 @@
+// Stage 1 of the two-stage reduction: batched dense -> band (half-width NB = 32) reduction of
+//   K1 = H_{-1} K H_{-1}   (H_{-1} ga = beta0 e_0)
+// by block Householder reflectors, with the Z-test block carried along (B <- Q^T S), and the
+// matching back-transformation  yb = -beta0 Q x.  Together with chase.cu / bandsolve.cu / gamma.cu
+// this replaces the reference's jnp.linalg.eigh(K) + V^T ga + V^T S + V c
+// (interpolatory.py:48-51, 76-80, 100); DESIGN.md section 3b, NumPy model: tests/twostage_model.py.
+//
+// Per panel p (columns c0 .. c0+NB-1, rows r0 = c0+NB .. n-1 below the band), all T matrices of the
+// batch in one launch each (blockIdx.y / .z = matrix):
+//   panel_qr_kernel  Householder QR of the (n-r0) x NB block, one thread-block CLUSTER per matrix:
+//                    the block lives in the distributed shared memory of the cluster, column norms
+//                    and v^T P are exchanged through DSMEM + cluster barriers.  Emits R (in place),
+//                    V (in place below R, and as a dense n x NB operand) and the compact-WY factor.
+//   symm_kernel      Y = A22 V on the FP64 tensor cores (DMMA m8n8k4), lower triangle only: each
+//                    CTA owns 128 rows and walks the row of tiles (direct left of the diagonal,
+//                    transposed right of it), cp.async double-buffered; epilogue V^T Y and V^T B partials
+//   reduce_kernel    fixed-order sum of the per-CTA partials (deterministic, no atomics)
+//   wform_kernel     W = (Y - 1/2 V T^T (V^T Y)) T,  B -= V T^T (V^T B)
+//   syr2k_kernel     A22 -= V W^T + W V^T on the lower tiles (DMMA, K = 2 NB)
+// Everything is GEMM-shaped: 4/3 n^3 flop on the tensor cores, the trailing matrix is read
+// 2x and written 1x per panel (n/NB panels) instead of once per column.
+#include <cooperative_groups.h>
+
+#include <stdlib.h>
+
+#include "internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace chd {
+
+constexpr int NB = CHD_BAND;
+constexpr int QR_THREADS = 256;
+constexpr int QR_S = NB + 1;        // shared-memory row stride of the panel slice
+constexpr int QR_MAXCS = 16;
+constexpr int QR_XW = NB + 2;       // exchange slot: NB values + (ssq, alpha)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ------------------------------------------------------------------ H_{-1}
+struct Refl0Args {
+  const double* ga;   // T x n
+  double* V;          // T x n x NB   (column 0 = v0, the rest 0)
+  double* v0;         // T x n
+  double* Tf;         // T x tf_stride (slot 0 = diag(tau0, 0, ...))
+  size_t tf_stride;
+  double* tau0;       // T
+  double* beta0;      // T
+  int n;
+};
+
+__global__ void __launch_bounds__(256) refl0_kernel(Refl0Args a) {
+  __shared__ double red[40];
+  const int t = blockIdx.x, tid = threadIdx.x, n = a.n;
+  const double* ga = a.ga + (size_t)t * n;
+  double ss = 0.0;
+  for (int i = 1 + tid; i < n; i += blockDim.x) ss += ga[i] * ga[i];
+  ss = block_sum(ss, red);
+  const double alpha = ga[0];
+  double beta, tau, scale;
+  if (ss == 0.0) {
+    beta = alpha; tau = 0.0; scale = 0.0;
+  } else {
+    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+    tau = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+  double* V = a.V + (size_t)t * n * NB;
+  double* v0 = a.v0 + (size_t)t * n;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double v = (i == 0) ? 1.0 : ga[i] * scale;
+    v0[i] = v;
+  }
+  for (int e = tid; e < n * NB; e += blockDim.x) {
+    const int i = e / NB, c = e % NB;
+    V[e] = (c == 0) ? ((i == 0) ? 1.0 : ga[i] * scale) : 0.0;
+  }
+  double* Tf = a.Tf + (size_t)t * a.tf_stride;
+  for (int e = tid; e < NB * NB; e += blockDim.x) Tf[e] = (e == 0) ? tau : 0.0;
+  if (tid == 0) { a.tau0[t] = tau; a.beta0[t] = beta; }
+}
+
+// ------------------------------------------------------------------ panel QR (cluster kernel)
+struct QrArgs {
+  double* A; size_t strideA; int ldk;
+  double* V;        // T x n x NB
+  double* Tf;       // T x tf_stride, already offset to this panel's slot
+  size_t tf_stride;
+  int n, r0, c0;
+  int RP;           // panel rows per CTA
+  int RS;           // of which kept in shared memory (the rest is worked on in place, in L2)
+};
+
+__global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(QrArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int g = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = QR_THREADS / 32;
+  const int n = a.n, r0 = a.r0, c0 = a.c0, ldk = a.ldk, RP = a.RP, RS = a.RS;
+  const int m = n - r0;
+  const int nref = min(NB, m - 1);
+  double* A = a.A + (size_t)t * a.strideA;
+
+  double* xch = smem;                              // 2 x QR_MAXCS x QR_XW
+  double* red = xch + 2 * QR_MAXCS * QR_XW;        // NW x QR_XW
+  double* mine = red + NW * QR_XW;                 // QR_XW
+  double* tot = mine + QR_XW;                      // QR_XW
+  double* ws = tot + QR_XW;                        // NB
+  double* taus = ws + NB;                          // NB
+  double* Gs = taus + NB;                          // NB x QR_S   G[c][t] = v_c . v_t (c < t)
+  double* Ts = Gs + NB * QR_S;                     // NB x QR_S
+  double* Ps = Ts + NB * QR_S;                     // RS x QR_S
+
+  const int pr0 = g * RP;
+  const int nrows = max(0, min(m - pr0, RP));
+  double* Ag = A + (size_t)(r0 + pr0) * ldk + c0;  // first owned row, first panel column
+  auto rowp = [&](int lr) -> double* { return (lr < RS) ? (Ps + lr * QR_S) : (Ag + (size_t)lr * ldk); };
+
+  for (int e = tid; e < min(nrows, RS) * NB; e += QR_THREADS) {
+    const int lr = e / NB, c = e % NB;
+    Ps[lr * QR_S + c] = Ag[(size_t)lr * ldk + c];
+  }
+  for (int e = tid; e < NB * QR_S; e += QR_THREADS) { Gs[e] = 0.0; Ts[e] = 0.0; }
+  if (tid < NB) taus[tid] = 0.0;
+  __syncthreads();
+
+  int par = 0;
+  // exchange `nv` doubles of `mine` with every CTA of the cluster; afterwards tot[] holds the fixed-order sums
+  auto exchange = [&](int nv) {
+    if (CS == 1) {
+      __syncthreads();
+      if (tid < nv) tot[tid] = mine[tid];
+      __syncthreads();
+      return;
+    }
+    __syncthreads();
+    for (int e = tid; e < CS * nv; e += QR_THREADS) {
+      const int dst = e / nv, q = e % nv;
+      double* remote = cluster.map_shared_rank(xch + (par * QR_MAXCS + g) * QR_XW, dst);
+      remote[q] = mine[q];
+    }
+    cluster.sync();
+    if (tid < nv) {
+      double s = 0.0;
+      for (int q = 0; q < CS; ++q) s += xch[(par * QR_MAXCS + q) * QR_XW + tid];
+      tot[tid] = s;
+    }
+    par ^= 1;
+    __syncthreads();
+  };
+
+  // norm of column 0 below its diagonal and the diagonal element
+  {
+    double sq = 0.0, al = 0.0;
+    for (int lr = tid; lr < nrows; lr += QR_THREADS) {
+      const int pr = pr0 + lr;
+      const double x = rowp(lr)[0];
+      if (pr > 0) sq += x * x; else al = x;
+    }
+    sq = warp_sum(sq); al = warp_sum(al);
+    if (lane == 0) { red[wid * QR_XW] = sq; red[wid * QR_XW + 1] = al; }
+    __syncthreads();
+    if (tid < 2) {
+      double s = 0.0;
+      for (int w = 0; w < NW; ++w) s += red[w * QR_XW + tid];
+      mine[tid] = s;
+    }
+    exchange(2);
+  }
+
+  for (int tc = 0; tc < nref; ++tc) {
+    const double ssq = tot[0], alpha = tot[1];
+    double beta, tau, scale;
+    if (ssq == 0.0) {
+      beta = alpha; tau = 0.0; scale = 0.0;
+    } else {
+      beta = -copysign(sqrt(alpha * alpha + ssq), alpha);
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    __syncthreads();   // everybody has read tot[]
+    if (tid == 0) taus[tc] = tau;
+    // ---- w[c] = sum_r v[r] P[r][c]   (lanes c > tc); lanes c < tc get G[c][tc] = v_c . v_tc for free
+    {
+      double acc = 0.0;
+      for (int lr = wid; lr < nrows; lr += NW) {
+        const int pr = pr0 + lr;
+        if (pr < tc) continue;
+        const double* row = rowp(lr);
+        const double vr = (pr == tc) ? 1.0 : row[tc] * scale;
+        // columns c < tc hold v_c in place (rows pr > c; here pr >= tc > c)
+        acc = fma(vr, row[lane], acc);
+      }
+      red[wid * QR_XW + lane] = acc;
+      __syncthreads();
+      if (tid < NB) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += red[w * QR_XW + tid];
+        mine[tid] = s;
+      }
+      exchange(NB);
+      if (tid < NB) {
+        ws[tid] = (tid > tc) ? tau * tot[tid] : 0.0;
+        if (tid < tc) Gs[tid * QR_S + tc] = tot[tid];
+      }
+      __syncthreads();
+    }
+    // ---- P[:, c > tc] -= v w^T, v stored in place; norm / diagonal of the next column on the fly
+    {
+      const bool more = (tc + 1 < nref);
+      double sq = 0.0, al = 0.0;
+      const double wl = ws[lane];
+      for (int lr = wid; lr < nrows; lr += NW) {
+        const int pr = pr0 + lr;
+        if (pr < tc) continue;
+        double* row = rowp(lr);
+        const double vr = (pr == tc) ? 1.0 : row[tc] * scale;
+        __syncwarp();
+        if (lane > tc) {
+          const double x = row[lane] - vr * wl;
+          row[lane] = x;
+          if (lane == tc + 1) {
+            if (pr > tc + 1) sq = fma(x, x, sq);
+            else if (pr == tc + 1) al = x;
+          }
+        } else if (lane == tc) {
+          row[tc] = (pr == tc) ? beta : vr;
+        }
+      }
+      if (more) {
+        sq = __shfl_sync(0xffffffffu, sq, tc + 1);
+        al = __shfl_sync(0xffffffffu, al, tc + 1);
+        if (lane == 0) { red[wid * QR_XW] = sq; red[wid * QR_XW + 1] = al; }
+        __syncthreads();
+        if (tid < 2) {
+          double s = 0.0;
+          for (int w = 0; w < NW; ++w) s += red[w * QR_XW + tid];
+          mine[tid] = s;
+        }
+        exchange(2);
+      } else {
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- compact-WY factor: T[t][t] = tau_t, T[:t, t] = -tau_t T[:t,:t] G[:t, t]   (dlarft, forward columnwise)
+  if (wid == 0) {
+    for (int tc = 0; tc < nref; ++tc) {
+      const double tau = taus[tc];
+      double s = 0.0;
+      if (lane < tc)
+        for (int k = lane; k < tc; ++k) s = fma(Ts[lane * QR_S + k], Gs[k * QR_S + tc], s);
+      __syncwarp();
+      if (lane < tc) Ts[lane * QR_S + tc] = -tau * s;
+      if (lane == tc) Ts[tc * QR_S + tc] = tau;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (g == 0) {
+    double* Tf = a.Tf + (size_t)t * a.tf_stride;
+    for (int e = tid; e < NB * NB; e += QR_THREADS) Tf[e] = Ts[(e / NB) * QR_S + (e % NB)];
+  }
+  // ---- outputs: the factored block in place (R over V), V as a dense operand
+  double* V = a.V + (size_t)t * n * NB + (size_t)(r0 + pr0) * NB;
+  for (int e = tid; e < nrows * NB; e += QR_THREADS) {
+    const int lr = e / NB, c = e % NB, pr = pr0 + lr;
+    const double x = rowp(lr)[c];
+    if (lr < RS) Ag[(size_t)lr * ldk + c] = x;
+    V[e] = (c >= nref || pr < c) ? 0.0 : ((pr == c) ? 1.0 : x);
+  }
+  if (CS > 1) cluster.sync();   // no CTA may exit while its shared memory can still be written remotely
+}
+
+// ------------------------------------------------------------------ Y = A22 V
+constexpr int SY_BM = 128, SY_KC = 32;
+constexpr int SY_SD = SY_KC + 4;    // direct tile [i][k] stride (== 4 mod 8: conflict-free fragment loads)
+constexpr int SY_ST = SY_BM + 8;    // transposed tile [k][i] stride (== 8 mod 16)
+constexpr int SY_SV = NB + 8;       // V chunk [k][c] stride (== 8 mod 16)
+constexpr int SY_TILE = (SY_BM * SY_SD > SY_KC * SY_ST) ? SY_BM * SY_SD : SY_KC * SY_ST;
+constexpr int SY_STAGE = SY_TILE + SY_KC * SY_SV;
+constexpr int SY_NST = 2;
+constexpr int SY_ZW = 128;          // padded width of the Z-block partials
+
+struct SymmArgs {
+  const double* A; size_t strideA; int ldk;
+  const double* V;   // T x n x NB
+  double* Y;         // T x n x NB
+  const double* Bq;  // T x n x ldb or null
+  int ldb, nz;
+  double* Mpart;     // T x nblk x NB x NB
+  double* Zpart;     // T x nblk x NB x SY_ZW
+  int n, r0, nblk;
+};
+
+__global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int t = blockIdx.y, bx = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = a.n, r0 = a.r0, ldk = a.ldk;
+  const double* A = a.A + (size_t)t * a.strideA;
+  const double* V = a.V + (size_t)t * n * NB;
+  const int i0 = r0 + SY_BM * bx;
+  const int m = n - r0;
+  const int nq = (m + SY_KC - 1) / SY_KC;
+  const int qd0 = (i0 - r0) / SY_KC;
+  const int nd = min(SY_BM / SY_KC, nq - qd0);
+  const int niter = nq + nd;
+
+  // iteration -> (chunk, transposed, masked)
+  auto decode = [&](int it, int& q, bool& tr, bool& mk) {
+    if (it < qd0) { q = it; tr = false; mk = false; }
+    else if (it < qd0 + nd) { q = it; tr = false; mk = true; }
+    else if (it < qd0 + 2 * nd) { q = it - nd; tr = true; mk = true; }
+    else { q = it - nd; tr = true; mk = false; }
+  };
+  auto issue = [&](int it) {
+    int q; bool tr, mk;
+    decode(it, q, tr, mk);
+    (void)mk;
+    double* tile = smem + (size_t)(it % SY_NST) * SY_STAGE;
+    double* vs = tile + SY_TILE;
+    const int j0 = r0 + SY_KC * q;
+    if (!tr) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int c = tid + 256 * s, row = c >> 4, part = c & 15;
+        const bool ok = (i0 + row < n) && (j0 + 2 * part < n);
+        const double* src = ok ? A + (size_t)(i0 + row) * ldk + j0 + 2 * part : A;
+        cp_async16(tile + row * SY_SD + 2 * part, src, ok);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int c = tid + 256 * s, row = c >> 6, part = c & 63;
+        const bool ok = (j0 + row < n) && (i0 + 2 * part < n);
+        const double* src = ok ? A + (size_t)(j0 + row) * ldk + i0 + 2 * part : A;
+        cp_async16(tile + row * SY_ST + 2 * part, src, ok);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int c = tid + 256 * s, row = c >> 4, part = c & 15;
+      const bool ok = (j0 + row < n);
+      const double* src = ok ? V + (size_t)(j0 + row) * NB + 2 * part : V;
+      cp_async16(vs + row * SY_SV + 2 * part, src, ok);
+    }
+  };
+
+  double acc[2][4][2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+
+  issue(0);
+  cp_async_commit();
+  for (int it = 0; it < niter; ++it) {
+    if (it + 1 < niter) issue(it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    int q; bool tr, mk;
+    decode(it, q, tr, mk);
+    const double* tile = smem + (size_t)(it % SY_NST) * SY_STAGE;
+    const double* vs = tile + SY_TILE;
+    const int j0 = r0 + SY_KC * q;
+#pragma unroll
+    for (int kk = 0; kk < SY_KC; kk += 4) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int y = 0; y < 4; ++y) bf[y] = vs[(kk + fk) * SY_SV + y * 8 + fr];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int rl = 16 * wid + 8 * x + fr;
+        af[x] = tr ? tile[(kk + fk) * SY_ST + rl] : tile[rl * SY_SD + kk + fk];
+        if (mk) {
+          const int i = i0 + rl, j = j0 + kk + fk;
+          if (tr ? (j <= i) : (j > i)) af[x] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: Y rows, then the partial products V_I^T Y_I and V_I^T B_I of this row block
+  double* Ys = smem;                       // SY_BM x (NB + 1)
+  double* Vs = Ys + SY_BM * (NB + 1);      // SY_BM x (NB + 1)
+  double* Y = a.Y + (size_t)t * n * NB;
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const int rl = 16 * wid + 8 * x + fr, i = i0 + rl;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int c = y * 8 + 2 * fk;
+      Ys[rl * (NB + 1) + c] = acc[x][y][0];
+      Ys[rl * (NB + 1) + c + 1] = acc[x][y][1];
+      if (i < n) *reinterpret_cast<double2*>(Y + (size_t)i * NB + c) = make_double2(acc[x][y][0], acc[x][y][1]);
+    }
+  }
+  for (int e = tid; e < SY_BM * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    Vs[rl * (NB + 1) + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * NB + c] : 0.0;
+  }
+  __syncthreads();
+  {
+    double mp[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int rl = 0; rl < SY_BM; ++rl) {
+      const double yv = Ys[rl * (NB + 1) + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mp[u] = fma(Vs[rl * (NB + 1) + wid + 8 * u], yv, mp[u]);
+    }
+    double* Mp = a.Mpart + ((size_t)t * a.nblk + bx) * NB * NB;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Mp[(wid + 8 * u) * NB + lane] = mp[u];
+  }
+  if (a.Bq && a.nz > 0) {
+    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
+    const int z = tid & 127, c1g = tid >> 7;   // 2 groups of 16 reflector columns
+    double zp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) zp[u] = 0.0;
+    if (z < a.nz) {
+      for (int rl = 0; rl < SY_BM && i0 + rl < n; ++rl) {
+        const double bv = Bq[(size_t)(i0 + rl) * a.ldb + z];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[rl * (NB + 1) + 16 * c1g + u], bv, zp[u]);
+      }
+    }
+    double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
+  }
+}
+
+// ------------------------------------------------------------------ fixed-order reduction of the partials
+struct ReduceArgs {
+  const double* Mpart; const double* Zpart;
+  double* Mred;   // T x NB x NB
+  double* Zred;   // T x NB x SY_ZW
+  int nblk, has_z;
+};
+
+__global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
+  const int t = blockIdx.y;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  constexpr int NM = NB * NB, NZ = NB * SY_ZW;
+  if (e < NM) {
+    const double* p = a.Mpart + (size_t)t * a.nblk * NM + e;
+    double s = 0.0;
+    for (int b = 0; b < a.nblk; ++b) s += p[(size_t)b * NM];
+    a.Mred[(size_t)t * NM + e] = s;
+  } else if (e < NM + NZ && a.has_z) {
+    const int ez = e - NM;
+    const double* p = a.Zpart + (size_t)t * a.nblk * NZ + ez;
+    double s = 0.0;
+    for (int b = 0; b < a.nblk; ++b) s += p[(size_t)b * NZ];
+    a.Zred[(size_t)t * NZ + ez] = s;
+  }
+}
+
+// ------------------------------------------------------------------ W and the Z-block update
+struct WformArgs {
+  const double* V; const double* Y; double* W;   // T x n x NB
+  const double* Tf; size_t tf_stride;            // this panel's slot
+  const double* Mred; const double* Zred;
+  double* Bq; int ldb, nz;
+  int n, r0;
+};
+
+constexpr int WF_BM = 64;
+constexpr size_t WF_SMEM = (3 * NB * (NB + 1) + NB * SY_ZW + 2 * WF_BM * (NB + 1)) * sizeof(double);
+
+__global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* Ts = smem;                        // NB x (NB + 1)
+  double* TM = Ts + NB * (NB + 1);          // T^T M
+  double* Ms = TM + NB * (NB + 1);
+  double* TZ = Ms + NB * (NB + 1);          // NB x SY_ZW
+  double* Vs = TZ + NB * SY_ZW;             // WF_BM x (NB + 1)
+  double* Xs = Vs + WF_BM * (NB + 1);
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = a.n, i0 = a.r0 + WF_BM * blockIdx.x;
+  const double* Tf = a.Tf + (size_t)t * a.tf_stride;
+  const double* V = a.V + (size_t)t * n * NB;
+  const double* Y = a.Y + (size_t)t * n * NB;
+  double* W = a.W + (size_t)t * n * NB;
+  const bool hz = a.Bq && a.nz > 0;
+  for (int e = tid; e < NB * NB; e += 256) {
+    Ts[(e / NB) * (NB + 1) + (e % NB)] = Tf[e];
+    Ms[(e / NB) * (NB + 1) + (e % NB)] = a.Mred[(size_t)t * NB * NB + e];
+  }
+  for (int e = tid; e < WF_BM * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    const bool ok = i0 + rl < n;
+    Vs[rl * (NB + 1) + c] = ok ? V[(size_t)(i0 + rl) * NB + c] : 0.0;
+    Xs[rl * (NB + 1) + c] = ok ? Y[(size_t)(i0 + rl) * NB + c] : 0.0;
+  }
+  __syncthreads();
+  // TM[a][c] = sum_{k <= a} T[k][a] M[k][c]
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int ar = e / NB, c = e % NB;
+    double s = 0.0;
+    for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], Ms[k * (NB + 1) + c], s);
+    TM[ar * (NB + 1) + c] = s;
+  }
+  if (hz) {
+    // TZ[a][z] = sum_{k <= a} T[k][a] Zred[k][z]
+    const double* Zr = a.Zred + (size_t)t * NB * SY_ZW;
+    for (int e = tid; e < NB * SY_ZW; e += 256) {
+      const int ar = e / SY_ZW, z = e % SY_ZW;
+      double s = 0.0;
+      for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], Zr[k * SY_ZW + z], s);
+      TZ[e] = s;
+    }
+  }
+  __syncthreads();
+  // X1 = Y - 1/2 V TM   (in place in Xs; each thread owns whole elements, rows wid + 8 q)
+  double x1[WF_BM / 8];
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) {
+    const int rl = wid + 8 * q;
+    double s = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < NB; ++k) s = fma(Vs[rl * (NB + 1) + k], TM[k * (NB + 1) + lane], s);
+    x1[q] = Xs[rl * (NB + 1) + lane] - 0.5 * s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) Xs[(wid + 8 * q) * (NB + 1) + lane] = x1[q];
+  __syncthreads();
+  // W = X1 T   (T upper triangular: k <= c)
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) {
+    const int rl = wid + 8 * q;
+    double s = 0.0;
+    for (int k = 0; k <= lane; ++k) s = fma(Xs[rl * (NB + 1) + k], Ts[k * (NB + 1) + lane], s);
+    if (i0 + rl < n) W[(size_t)(i0 + rl) * NB + lane] = s;
+  }
+  if (hz) {
+    double* Bq = a.Bq + (size_t)t * n * a.ldb;
+    const int z = tid & 127, hg = tid >> 7;
+    if (z < a.nz) {
+      for (int rl = hg; rl < WF_BM && i0 + rl < n; rl += 2) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < NB; ++k) s = fma(Vs[rl * (NB + 1) + k], TZ[k * SY_ZW + z], s);
+        Bq[(size_t)(i0 + rl) * a.ldb + z] -= s;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ A22 -= V W^T + W V^T  (lower tiles)
+constexpr int S2_BM = 128, S2_BN = 64, S2_K = 2 * NB;
+constexpr int S2_S = S2_K + 4;
+
+struct Syr2kArgs {
+  double* A; size_t strideA; int ldk;
+  const double* V; const double* W;
+  int n, r0;
+};
+
+__global__ void __launch_bounds__(256, 2) syr2k_kernel(Syr2kArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int t = blockIdx.z;
+  const int n = a.n, r0 = a.r0, ldk = a.ldk;
+  const int i0 = r0 + S2_BM * blockIdx.y, j0 = r0 + S2_BN * blockIdx.x;
+  if (j0 > i0 + S2_BM - 1) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  double* A = a.A + (size_t)t * a.strideA;
+  const double* V = a.V + (size_t)t * n * NB;
+  const double* W = a.W + (size_t)t * n * NB;
+  double* As = smem;                     // S2_BM x S2_S : [V_I | W_I]
+  double* Bs = As + S2_BM * S2_S;        // S2_BN x S2_S : [W_J | V_J]
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    const int c = tid + 256 * s, row = c >> 5, part = c & 31;
+    const bool ok = i0 + row < n;
+    const double* base = (part < 16) ? V : W;
+    const double* src = ok ? base + (size_t)(i0 + row) * NB + 2 * (part & 15) : base;
+    cp_async16(As + row * S2_S + 2 * part, src, ok);
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int c = tid + 256 * s, row = c >> 5, part = c & 31;
+    const bool ok = j0 + row < n;
+    const double* base = (part < 16) ? W : V;
+    const double* src = ok ? base + (size_t)(j0 + row) * NB + 2 * (part & 15) : base;
+    cp_async16(Bs + row * S2_S + 2 * part, src, ok);
+  }
+  cp_async_commit();
+  double acc[4][4][2];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+  const int wm = wid >> 1, wn = wid & 1;   // 4 x 2 warps, warp tile 32 x 32
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll 4
+  for (int kk = 0; kk < S2_K; kk += 4) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      af[x] = As[(32 * wm + 8 * x + fr) * S2_S + kk + fk];
+      bf[x] = Bs[(32 * wn + 8 * x + fr) * S2_S + kk + fk];
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int i = i0 + 32 * wm + 8 * x + fr;
+    if (i < n) {
+      double2 o[4];
+      bool full[4];
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const int j = j0 + 32 * wn + 8 * y + 2 * fk;
+        full[y] = (j + 1 <= i);
+        const double* p = A + (size_t)i * ldk + j;
+        if (full[y]) {
+          o[y] = ldcg2(reinterpret_cast<const double2*>(p));
+        } else {
+          o[y].x = (j <= i) ? ldcg(p) : 0.0;
+          o[y].y = 0.0;
+        }
+      }
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const int j = j0 + 32 * wn + 8 * y + 2 * fk;
+        double* p = A + (size_t)i * ldk + j;
+        if (full[y]) {
+          *reinterpret_cast<double2*>(p) = make_double2(o[y].x - acc[x][y][0], o[y].y - acc[x][y][1]);
+        } else if (j <= i) {
+          p[0] = o[y].x - acc[x][y][0];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ band extraction / padding
+// bandS[i][d] = T_b(i, i-d), d = 0..NB  (stride CHD_BAND_LD);  bandW: the same with room for the bulges
+// (2 NB sub-diagonals, stride CHD_CHASE_LD), zero filled.
+__global__ void band_extract_kernel(const double* __restrict__ A, size_t strideA, int ldk, int n,
+                                    double* __restrict__ bandS, double* __restrict__ bandW) {
+  const int t = blockIdx.y;
+  const double* At = A + (size_t)t * strideA;
+  double* bs = bandS + (size_t)t * n * CHD_BAND_LD;
+  double* bw = bandW ? bandW + (size_t)t * n * CHD_CHASE_LD : nullptr;
+  const size_t total = (size_t)n * CHD_CHASE_LD;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / CHD_CHASE_LD), d = (int)(e % CHD_CHASE_LD);
+    double v = 0.0;
+    if (d <= NB && i - d >= 0) v = At[(size_t)i * ldk + (i - d)];
+    if (bw) bw[e] = v;
+    if (d < CHD_BAND_LD) bs[(size_t)i * CHD_BAND_LD + d] = v;
+  }
+}
+
+__global__ void zero_pad_kernel(double* __restrict__ A, size_t strideA, int ldk, int n) {
+  double* At = A + (size_t)blockIdx.y * strideA;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int j = n; j < ldk; ++j) At[(size_t)i * ldk + j] = 0.0;
+}
+
+// ------------------------------------------------------------------ back-transformation  out = -beta0 Q x
+// Q = H_{-1} Q_0 Q_1 ...: block reflectors applied last to first, x <- x - V (T (V^T x)).  One cluster of
+// BT_CS CTAs per matrix; every CTA keeps its row slice of x in shared memory, V is read in place (below the
+// band of the factored matrix), the NB-vector V^T x is exchanged through DSMEM.
+constexpr int BT_CS = 8;
+constexpr int BT_THREADS = 512;
+
+struct Back2Args {
+  const double* A; size_t strideA; int ldk;
+  const double* Tf; size_t tf_stride;   // slot p = panel p (slot 0 = H_{-1})
+  const double* v0;     // T x n
+  const double* tau0;   // T
+  const double* x;      // T x n
+  const double* beta0;  // T
+  double* out; size_t out_stride;
+  int n, npanel;        // npanel = number of QR panels (slots 1..npanel)
+  int RPB;              // rows of x per CTA
+};
+
+__global__ void __cluster_dims__(BT_CS, 1, 1) __launch_bounds__(BT_THREADS) backtransform2_kernel(Back2Args a) {
+  extern __shared__ __align__(16) double smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int g = (int)cluster.block_rank();
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = BT_THREADS / 32;
+  const int n = a.n, ldk = a.ldk, RPB = a.RPB;
+  const double* A = a.A + (size_t)t * a.strideA;
+  double* xch = smem;                       // 2 x BT_CS x NB
+  double* red = xch + 2 * BT_CS * NB;       // NW x (NB + 1)
+  double* cs = red + NW * (NB + 1);         // NB   V^T x
+  double* ss = cs + NB;                     // NB   T (V^T x)
+  double* Ts = ss + NB;                     // NB x (NB + 1)
+  double* xs = Ts + NB * (NB + 1);          // RPB
+  const int row_lo = g * RPB, row_hi = min(n, row_lo + RPB);
+  for (int i = row_lo + tid; i < row_hi; i += BT_THREADS) xs[i - row_lo] = a.x[(size_t)t * n + i];
+  __syncthreads();
+  int par = 0;
+  for (int p = a.npanel; p >= 1; --p) {
+    const int r0 = p * NB, c0 = r0 - NB;
+    const int m = n - r0, nref = min(NB, m - 1);
+    const double* Tf = a.Tf + (size_t)t * a.tf_stride + (size_t)p * NB * NB;
+    for (int e = tid; e < NB * NB; e += BT_THREADS) Ts[(e / NB) * (NB + 1) + (e % NB)] = Tf[e];
+    const int lo = max(row_lo, r0);
+    // ---- c = V^T x over the owned rows: lanes = reflector columns, 4 rows in flight per warp iteration
+    double acc = 0.0;
+    for (int i = lo + wid; i < row_hi; i += NW) {
+      const int pr = i - r0;
+      double v = A[(size_t)i * ldk + c0 + lane];
+      if (pr < NB) v = (lane >= nref || pr < lane) ? 0.0 : ((pr == lane) ? 1.0 : v);
+      else if (lane >= nref) v = 0.0;
+      acc = fma(v, xs[i - row_lo], acc);
+    }
+    red[wid * (NB + 1) + lane] = acc;
+    __syncthreads();
+    if (tid < NB) {
+      double s = 0.0;
+      for (int w = 0; w < NW; ++w) s += red[w * (NB + 1) + tid];
+      for (int dst = 0; dst < BT_CS; ++dst) {
+        double* remote = cluster.map_shared_rank(xch + (par * BT_CS + g) * NB, dst);
+        remote[tid] = s;
+      }
+    }
+    cluster.sync();
+    if (tid < NB) {
+      double s = 0.0;
+      for (int q = 0; q < BT_CS; ++q) s += xch[(par * BT_CS + q) * NB + tid];
+      cs[tid] = s;
+    }
+    par ^= 1;
+    __syncthreads();
+    if (tid < NB) {
+      double s = 0.0;
+      for (int k = tid; k < NB; ++k) s = fma(Ts[tid * (NB + 1) + k], cs[k], s);
+      ss[tid] = s;
+    }
+    __syncthreads();
+    // ---- x -= V s
+    for (int i = lo + wid; i < row_hi; i += NW) {
+      const int pr = i - r0;
+      double v = A[(size_t)i * ldk + c0 + lane];
+      if (pr < NB) v = (lane >= nref || pr < lane) ? 0.0 : ((pr == lane) ? 1.0 : v);
+      else if (lane >= nref) v = 0.0;
+      double d = v * ss[lane];
+      d = warp_sum(d);
+      if (lane == 0) xs[i - row_lo] -= d;
+    }
+    __syncthreads();
+  }
+  // ---- H_{-1}
+  {
+    const double* v0 = a.v0 + (size_t)t * n;
+    double acc = 0.0;
+    for (int i = row_lo + tid; i < row_hi; i += BT_THREADS) acc = fma(v0[i], xs[i - row_lo], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) red[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < NW; ++w) s += red[w];
+      for (int dst = 0; dst < BT_CS; ++dst) {
+        double* remote = cluster.map_shared_rank(xch + (par * BT_CS + g) * NB, dst);
+        remote[0] = s;
+      }
+    }
+    cluster.sync();
+    double s = 0.0;
+    for (int q = 0; q < BT_CS; ++q) s += xch[(par * BT_CS + q) * NB];
+    const double f = a.tau0[t] * s, sc = -a.beta0[t];
+    for (int i = row_lo + tid; i < row_hi; i += BT_THREADS)
+      a.out[(size_t)t * a.out_stride + i] = sc * (xs[i - row_lo] - f * v0[i]);
+  }
+  cluster.sync();
+}
+
+// ------------------------------------------------------------------ host side
+int band_npanels(int n) {
+  // panels p = 1.. with r0 = p NB and at least two rows below the band
+  int np = 0;
+  while (n - (np + 1) * NB >= 2) ++np;
+  return np;
+}
+
+size_t band_workspace(const Plan* pl, int T) {
+  const size_t n = pl->n;
+  const size_t nblk = (n + SY_BM - 1) / SY_BM;
+  size_t b = 0;
+  b += 3 * align_up(T * n * NB * sizeof(double), 256);                       // V, Y, W
+  b += align_up((size_t)T * (band_npanels(pl->n) + 1) * NB * NB * sizeof(double), 256);   // T factors
+  b += align_up((size_t)T * nblk * NB * NB * sizeof(double), 256);           // Mpart
+  b += align_up((size_t)T * nblk * NB * SY_ZW * sizeof(double), 256);        // Zpart
+  b += align_up((size_t)T * NB * NB * sizeof(double), 256);                  // Mred
+  b += align_up((size_t)T * NB * SY_ZW * sizeof(double), 256);               // Zred
+  b += align_up(T * n * sizeof(double), 256);                                // v0
+  b += align_up(T * sizeof(double), 256);                                    // tau0
+  b += align_up((size_t)T * n * CHD_BAND_LD * sizeof(double), 256);          // bandS
+  b += align_up((size_t)T * n * CHD_CHASE_LD * sizeof(double), 256);         // bandW
+  return b + 4096;
+}
+
+bool band_carve(const Plan* pl, int T, Carver& cv, BandBuffers& bb) {
+  const size_t n = pl->n;
+  const size_t nblk = (n + SY_BM - 1) / SY_BM;
+  bb.V = cv.take<double>(T * n * NB);
+  bb.Y = cv.take<double>(T * n * NB);
+  bb.W = cv.take<double>(T * n * NB);
+  bb.tf_stride = (size_t)(band_npanels(pl->n) + 1) * NB * NB;
+  bb.Tf = cv.take<double>((size_t)T * bb.tf_stride);
+  bb.Mpart = cv.take<double>((size_t)T * nblk * NB * NB);
+  bb.Zpart = cv.take<double>((size_t)T * nblk * NB * SY_ZW);
+  bb.Mred = cv.take<double>((size_t)T * NB * NB);
+  bb.Zred = cv.take<double>((size_t)T * NB * SY_ZW);
+  bb.v0 = cv.take<double>(T * n);
+  bb.tau0 = cv.take<double>(T);
+  bb.bandS = cv.take<double>((size_t)T * n * CHD_BAND_LD);
+  bb.bandW = cv.take<double>((size_t)T * n * CHD_CHASE_LD);
+  return cv.ok;
+}
+
+static int g_qr_max_cs = -1;
+
+static int qr_cluster_size(const Plan* pl, int m, int& RP, int& RS, size_t& smem) {
+  // fixed part of the kernel's shared memory (doubles)
+  const size_t fixed = 2 * QR_MAXCS * QR_XW + (QR_THREADS / 32) * QR_XW + 2 * QR_XW + 2 * NB + 2 * NB * QR_S;
+  const size_t avail = (pl->smem_optin - fixed * sizeof(double)) / (QR_S * sizeof(double));
+  {
+    const char* e = getenv("CHD_QR_MAXCS");   // tuning / test switch: largest cluster the panel QR may use
+    g_qr_max_cs = e ? atoi(e) : 8;
+    if (g_qr_max_cs != 1 && g_qr_max_cs != 2 && g_qr_max_cs != 4 && g_qr_max_cs != 8 && g_qr_max_cs != 16)
+      g_qr_max_cs = 8;
+  }
+  int cs = 1;
+  while (cs < g_qr_max_cs && (m + cs - 1) / cs > 384) cs *= 2;
+  RP = (m + cs - 1) / cs;
+  RS = (int)((size_t)RP < avail ? (size_t)RP : avail);
+  smem = (fixed + (size_t)RS * QR_S) * sizeof(double);
+  return cs;
+}
+
+// Launches one panel's trailing work for V / Tf slot `slot` and trailing block starting at r0.
+static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B, int ldb, int nz, int r0, int slot,
+                           const BandBuffers& bb, cudaStream_t st) {
+  const int n = pl->n, m = n - r0;
+  const size_t strideA = (size_t)n * ldk;
+  const int nblk = (m + SY_BM - 1) / SY_BM;
+  {
+    SymmArgs a;
+    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Y = bb.Y; a.Bq = B; a.ldb = ldb; a.nz = nz;
+    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk;
+    symm_kernel<<<dim3(nblk, T), 256, SY_NST * SY_STAGE * sizeof(double), st>>>(a);
+    CHD_LAUNCHED();
+  }
+  {
+    ReduceArgs a;
+    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.Mred = bb.Mred; a.Zred = bb.Zred; a.nblk = nblk;
+    a.has_z = (B && nz > 0) ? 1 : 0;
+    const int total = NB * NB + (a.has_z ? NB * SY_ZW : 0);
+    reduce_kernel<<<dim3((total + 255) / 256, T), 256, 0, st>>>(a);
+    CHD_LAUNCHED();
+  }
+  {
+    WformArgs a;
+    a.V = bb.V; a.Y = bb.Y; a.W = bb.W; a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride;
+    a.Mred = bb.Mred; a.Zred = bb.Zred; a.Bq = B; a.ldb = ldb; a.nz = nz; a.n = n; a.r0 = r0;
+    wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
+    CHD_LAUNCHED();
+  }
+  {
+    Syr2kArgs a;
+    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.W = bb.W; a.n = n; a.r0 = r0;
+    const dim3 grid((m + S2_BN - 1) / S2_BN, (m + S2_BM - 1) / S2_BM, T);
+    syr2k_kernel<<<grid, 256, (S2_BM + S2_BN) * S2_S * sizeof(double), st>>>(a);
+    CHD_LAUNCHED();
+  }
+  return CHD_OK;
+}
+
+int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nz,
+                       double* beta0, const BandBuffers& bb, cudaStream_t st) {
+  const int n = pl->n;
+  if (nz > SY_ZW || (ldk & 1)) return CHD_EINVAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CHD_CUDA(cudaFuncSetAttribute(symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SY_NST * SY_STAGE * sizeof(double))));
+    CHD_CUDA(cudaFuncSetAttribute(syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((S2_BM + S2_BN) * S2_S * sizeof(double))));
+    CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+    CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
+    CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CHD_CUDA(cudaFuncSetAttribute(backtransform2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl->smem_optin));
+    attr_set = true;
+  }
+  const size_t strideA = (size_t)n * ldk;
+  if (ldk > n) {
+    zero_pad_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(K, strideA, ldk, n);
+    CHD_LAUNCHED();
+  }
+  {
+    Refl0Args a;
+    a.ga = ga; a.V = bb.V; a.v0 = bb.v0; a.Tf = bb.Tf; a.tf_stride = bb.tf_stride; a.tau0 = bb.tau0;
+    a.beta0 = beta0; a.n = n;
+    refl0_kernel<<<T, 256, 0, st>>>(a);
+    CHD_LAUNCHED();
+  }
+  int rc;
+  if ((rc = trailing_launch(pl, K, ldk, T, B, ldb, nz, 0, 0, bb, st))) return rc;
+  const int np = band_npanels(n);
+  for (int p = 1; p <= np; ++p) {
+    const int r0 = p * NB, c0 = r0 - NB, m = n - r0;
+    QrArgs a;
+    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Tf = bb.Tf + (size_t)p * NB * NB;
+    a.tf_stride = bb.tf_stride; a.n = n; a.r0 = r0; a.c0 = c0;
+    size_t smem;
+    const int cs = qr_cluster_size(pl, m, a.RP, a.RS, smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs, T);
+    cfg.blockDim = dim3(QR_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_kernel, a));
+    g_launches.fetch_add(1);
+    if ((rc = trailing_launch(pl, K, ldk, T, B, ldb, nz, r0, p, bb, st))) return rc;
+  }
+  band_extract_kernel<<<dim3(min((n * CHD_CHASE_LD + 255) / 256, 1024), T), 256, 0, st>>>(K, strideA, ldk, n,
+                                                                                             bb.bandS, bb.bandW);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+int backtransform2_launch(const Plan* pl, const double* K, int ldk, const BandBuffers& bb, const double* x,
+                          const double* beta0, double* out, size_t out_stride, int T, cudaStream_t st) {
+  Back2Args a;
+  a.A = K; a.strideA = (size_t)pl->n * ldk; a.ldk = ldk; a.Tf = bb.Tf; a.tf_stride = bb.tf_stride; a.v0 = bb.v0;
+  a.tau0 = bb.tau0; a.x = x; a.beta0 = beta0; a.out = out; a.out_stride = out_stride; a.n = pl->n;
+  a.npanel = band_npanels(pl->n);
+  a.RPB = (pl->n + BT_CS - 1) / BT_CS;
+  const size_t smem = (2 * BT_CS * NB + (BT_THREADS / 32) * (NB + 1) + 2 * NB + NB * (NB + 1) + a.RPB) * sizeof(double);
+  backtransform2_kernel<<<dim3(BT_CS, T), BT_THREADS, smem, st>>>(a);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+}  // namespace chd

@@ -1,0 +1,218 @@
+// Stage 2 of the two-stage reduction: symmetric band (half-width NB) -> tridiagonal, VALUES ONLY, by Householder
+// bulge chasing (Murata-Horikoshi / Lang), batched over the T matrices of a launch.  The transformations never
+// touch row/column 0, so e_0 is preserved and the loss of interpolatory.py:124-126 only needs the resulting
+// (d, e) together with beta0 (gamma.cu); nothing that needs vectors goes through this stage (bandsolve.cu solves
+// in band coordinates), so no reflector is stored or applied to anything but the band itself.
+// NumPy model: tests/twostage_model.py::stage2.
+//
+// Parallelisation: sweep j (annihilate column j below the sub-diagonal, chase the bulge to the bottom) is owned
+// by one warp; warps of a matrix take sweeps round-robin and run as a software pipeline: hop h of sweep j+1 may
+// start once sweep j has finished hop h+1 (progress counters in global memory, release/acquire).  The working
+// band (2 NB sub-diagonals, 4.3 MB per matrix at n = 8192) stays in L2.
+#include <cooperative_groups.h>
+
+#include "internal.cuh"
+
+namespace chd {
+
+constexpr int CB = CHD_BAND;
+constexpr int CLD = CHD_CHASE_LD;
+constexpr int CS_ = CB + 1;               // shared-memory stride of the dense blocks
+constexpr int CH_WARPS = 4;
+constexpr int CH_DONE = 1 << 30;
+
+struct ChaseArgs {
+  double* bandW;   // T x n x CLD, bandW[i][d] = A(i, i-d)
+  int* prog;       // T x n   hops finished by sweep j
+  int n;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Householder from the warp-distributed vector x (lane l < len holds x[l]); returns v (v[0] = 1), tau, beta.
+__device__ __forceinline__ void warp_reflector(double x, int lane, int len, double& v, double& tau, double& beta) {
+  const double alpha = __shfl_sync(0xffffffffu, x, 0);
+  double ss = (lane >= 1 && lane < len) ? x * x : 0.0;
+  ss = warp_sum(ss);
+  if (ss == 0.0) {
+    beta = alpha; tau = 0.0;
+    v = (lane == 0) ? 1.0 : 0.0;
+  } else {
+    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+    tau = (beta - alpha) / beta;
+    const double scale = 1.0 / (alpha - beta);
+    v = (lane == 0) ? 1.0 : ((lane < len) ? x * scale : 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t = blockIdx.y, n = a.n;
+  const int W = gridDim.x * CH_WARPS, w = blockIdx.x * CH_WARPS + wid;
+  double* bw = a.bandW + (size_t)t * n * CLD;
+  int* prog = a.prog + (size_t)t * n;
+  double* D = smem + (size_t)wid * (2 * CB * CS_ + 3 * CB);   // CB x CS_
+  double* S = D + CB * CS_;                                   // CB x CS_
+  double* vs = S + CB * CS_;                                  // CB
+  double* ws = vs + CB;                                       // CB
+  double* v2s = ws + CB;                                      // CB
+
+  for (int j = w; j <= n - 3; j += W) {
+    int lo = j + 1, hi = min(j + CB, n - 1);
+    int len = hi - lo + 1;
+    int h = 0;
+    auto wait_prev = [&](int need) {
+      if (j == 0) return;
+      if (lane == 0) {
+        while (ld_acquire(prog + j - 1) < need) __nanosleep(40);
+      }
+      __syncwarp();
+    };
+    wait_prev(2);
+    // first reflector of the sweep: column j, rows lo..hi
+    double v, tau, beta;
+    {
+      const double x = (lane < len) ? __ldcg(bw + (size_t)(lo + lane) * CLD + (lane + 1)) : 0.0;
+      warp_reflector(x, lane, len, v, tau, beta);
+      if (lane < len) __stcg(bw + (size_t)(lo + lane) * CLD + (lane + 1), (lane == 0) ? beta : 0.0);
+    }
+    while (true) {
+      // ---------------- diagonal block D = A[lo..hi, lo..hi]  <- H D H
+      for (int l = 0; l < CB; ++l) {
+        // row l, lanes = d (column l - d)
+        double x = 0.0;
+        if (l < len && lane <= l) x = __ldcg(bw + (size_t)(lo + l) * CLD + lane);
+        if (lane <= l) {
+          D[l * CS_ + (l - lane)] = x;
+          D[(l - lane) * CS_ + l] = x;
+        }
+      }
+      vs[lane] = v;
+      __syncwarp();
+      double p = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < CB; ++c) p = fma(D[lane * CS_ + c], vs[c], p);
+      p *= tau;
+      const double al = -0.5 * tau * warp_sum(p * v);
+      const double wv = p + al * v;
+      ws[lane] = wv;
+      __syncwarp();
+#pragma unroll 8
+      for (int c = 0; c < CB; ++c) D[lane * CS_ + c] -= v * ws[c] + wv * vs[c];
+      __syncwarp();
+      for (int l = 0; l < len; ++l)
+        if (lane <= l) __stcg(bw + (size_t)(lo + l) * CLD + lane, D[l * CS_ + (l - lane)]);
+      // ---------------- block below: S = A[lo2..hi2, lo..hi]  <- S H, then the next reflector from its first column
+      const int lo2 = hi + 1, hi2 = min(hi + CB, n - 1);
+      const int len2 = hi2 - lo2 + 1;
+      bool last = (len2 <= 0);
+      double v2 = 0.0, tau2 = 0.0;
+      if (!last) {
+        const int off = lo2 - lo;   // == len
+        for (int l = 0; l < CB; ++l) {
+          // row l of S, lanes = column c: A(lo2+l, lo+c) at d = off + l - c
+          double x = 0.0;
+          if (l < len2 && lane < len) x = __ldcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane));
+          S[l * CS_ + lane] = x;
+        }
+        __syncwarp();
+        double u = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < CB; ++c) u = fma(S[lane * CS_ + c], vs[c], u);
+        u *= tau;
+#pragma unroll 8
+        for (int c = 0; c < CB; ++c) S[lane * CS_ + c] -= u * vs[c];
+        __syncwarp();
+        if (len2 >= 2) {
+          double beta2;
+          const double x = S[lane * CS_ + 0];
+          warp_reflector(x, lane, len2, v2, tau2, beta2);
+          v2s[lane] = v2;
+          S[lane * CS_ + 0] = (lane == 0) ? beta2 : 0.0;
+          __syncwarp();
+          // z[c] = tau2 sum_l v2[l] S[l][c]  (lane = column c >= 1), S[l][c] -= v2[l] z[c]
+          if (lane >= 1) {
+            double z = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < CB; ++l) z = fma(v2s[l], S[l * CS_ + lane], z);
+            z *= tau2;
+#pragma unroll 8
+            for (int l = 0; l < CB; ++l) S[l * CS_ + lane] -= v2s[l] * z;
+          }
+          __syncwarp();
+        } else {
+          last = true;
+        }
+        for (int l = 0; l < len2; ++l)
+          if (lane < len) __stcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane), S[l * CS_ + lane]);
+      }
+      // ---------------- publish progress, move on
+      __syncwarp();
+      ++h;
+      if (lane == 0) {
+        __threadfence();
+        st_release(prog + j, last ? CH_DONE : h);
+      }
+      if (last) break;
+      v = v2; tau = tau2; lo = lo2; hi = hi2; len = len2;
+      wait_prev(h + 2);
+    }
+  }
+}
+
+__global__ void chase_extract_kernel(const double* __restrict__ bandW, int n, double* __restrict__ d,
+                                     double* __restrict__ e) {
+  const int t = blockIdx.y;
+  const double* bw = bandW + (size_t)t * n * CLD;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    d[(size_t)t * n + i] = bw[(size_t)i * CLD];
+    e[(size_t)t * n + i] = (i + 1 < n) ? bw[(size_t)(i + 1) * CLD + 1] : 0.0;
+  }
+}
+
+size_t chase_workspace(const Plan* pl, int T) { return align_up((size_t)T * pl->n * sizeof(int), 256) + 256; }
+
+int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e, int T, cudaStream_t st) {
+  const int n = pl->n;
+  const size_t smem = (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double);
+  static int max_ctas_per_sm = -1;
+  if (max_ctas_per_sm < 0) {
+    CHD_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_kernel, CH_WARPS * 32, smem));
+    max_ctas_per_sm = nb > 0 ? nb : 1;
+  }
+  if (n >= 3) {
+    CHD_CUDA(cudaMemsetAsync(prog, 0, (size_t)T * n * sizeof(int), st));
+    // warps per matrix: all of them co-resident (the pipeline spins on its predecessors), at most the
+    // pipeline depth n / (2 NB)
+    const int cap = pl->sm_count * max_ctas_per_sm;        // CTAs
+    int per = cap / T;
+    const int want = (n / (2 * CB) + CH_WARPS) / CH_WARPS;
+    if (per > want) per = want;
+    if (per < 1) per = 1;
+    for (int t0 = 0; t0 < T; ) {
+      int cnt = cap / per;
+      if (cnt > T - t0) cnt = T - t0;
+      ChaseArgs a;
+      a.bandW = bandW + (size_t)t0 * n * CLD; a.prog = prog + (size_t)t0 * n; a.n = n;
+      void* params[] = {&a};
+      CHD_CUDA(cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(per, cnt), dim3(CH_WARPS * 32), params, smem, st));
+      g_launches.fetch_add(1);
+      t0 += cnt;
+    }
+  }
+  chase_extract_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(bandW, n, d, e);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+}  // namespace chd

@@ -27,6 +27,8 @@ void set_error(const char* fmt, ...);
     CHD_CUDA(cudaGetLastError());               \
   } while (0)
 
+#define CHD_CHASE_LD 66    /* row stride of the bulge-chasing work band (2 CHD_BAND sub-diagonals) */
+
 struct Plan {
   int n, N, C, device;
   int sm_count;
@@ -36,6 +38,7 @@ struct Plan {
   int threads;    // threads per CTA of the tridiagonalisation (256: two CTAs per SM, 512: one)
   int bulk;       // symv data path: 1 = cp.async.bulk tile ring, 0 = register loads
   int rows_per_chunk;
+  int two_stage;  // 1: dense -> band -> tridiagonal (band.cu / chase.cu / bandsolve.cu), 0: one-stage tridiag.cu
   size_t smem_optin;
 };
 

@@ -151,6 +151,8 @@ struct FinishArgs {
   size_t out_stride;
   int32_t* status;
   int n;
+  double* gu_out;       // T or null.  Not null: two-stage path -- gamma_used is handed to bandsolve.cu, which does the
+                        // solve and the Z-test in band coordinates; this kernel stops after the gamma search
 };
 
 __global__ void __launch_bounds__(256) gamma_finish_kernel(FinishArgs a) {
@@ -289,6 +291,14 @@ __global__ void __launch_bounds__(256) gamma_finish_kernel(FinishArgs a) {
 
   // final solve with gamma_used = max(gamma, gamma_min)  (REG:52, 76-80)
   const double gu = isnan(gamma) ? gamma : fmax(gamma, gmin);
+  if (a.gu_out) {
+    if (tid == 0) {
+      a.gu_out[t] = gu;
+      a.gamma[(size_t)t * a.out_stride] = gamma;
+      a.status[t] = st;
+    }
+    return;
+  }
   double* eta = a.eta + (size_t)t * n;
   double* uu = a.uu + (size_t)t * n;
   double* xs = a.x + (size_t)t * n;
@@ -362,7 +372,7 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
                  double* loss, double* B, int ldb, int nz, int gamma_min_mode, double gamma_min_base,
                  double* gamma_min, int want_lambda_min, double* lambda_min, double* eta, double* uu, double* x,
                  double* noise, double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status,
-                 int T, cudaStream_t st) {
+                 int T, cudaStream_t st, double* gu_out) {
   const int n = pl->n;
   gamma_grid_kernel<<<dim3((CHD_GRID_POINTS + GR_THREADS - 1) / GR_THREADS, T), GR_THREADS, 0, st>>>(
       d, e, n, grid, CHD_GRID_POINTS, loss);
@@ -372,7 +382,7 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
   a.B = B; a.ldb = ldb; a.nz = nz; a.gamma_min_mode = gamma_min_mode; a.gamma_min_base = gamma_min_base;
   a.gamma_min = gamma_min; a.want_lambda_min = want_lambda_min; a.lambda_min = lambda_min;
   a.eta = eta; a.uu = uu; a.x = x; a.noise = noise; a.z_low = z_low; a.z_high = z_high; a.gamma = gamma;
-  a.out_stride = out_stride; a.status = status; a.n = n;
+  a.out_stride = out_stride; a.status = status; a.n = n; a.gu_out = gu_out;
   gamma_finish_kernel<<<T, 256, 0, st>>>(a);
   CHD_LAUNCHED();
   return CHD_OK;

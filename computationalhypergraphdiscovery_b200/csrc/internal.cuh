@@ -20,11 +20,28 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
                  double* loss, double* B, int ldb, int nz, int gamma_min_mode, double gamma_min_base,
                  double* gamma_min, int want_lambda_min, double* lambda_min, double* eta, double* uu, double* x,
                  double* noise, double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status,
-                 int T, cudaStream_t st);
+                 int T, cudaStream_t st, double* gu_out = nullptr);
 int gamma_band_launch(const Plan* pl, int B, const double* band, const double* gt, const double* grid, double* loss,
                       double* Bq, int ldb, int nz, int gamma_min_mode, double gamma_min_base, double* gamma_min,
                       int want_lambda_min, double* lambda_min, double* Dg, double* Ug, double* x, double* noise,
                       double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status, int T,
+                      cudaStream_t st);
+// ---- two-stage reduction (band.cu, chase.cu, bandsolve.cu)
+struct BandBuffers {
+  double *V, *Y, *W, *Tf, *Mpart, *Zpart, *Mred, *Zred, *v0, *tau0, *bandS, *bandW;
+  size_t tf_stride;
+};
+int band_npanels(int n);
+size_t band_workspace(const Plan* pl, int T);
+bool band_carve(const Plan* pl, int T, Carver& cv, BandBuffers& bb);
+int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nz,
+                       double* beta0, const BandBuffers& bb, cudaStream_t st);
+int backtransform2_launch(const Plan* pl, const double* K, int ldk, const BandBuffers& bb, const double* x,
+                          const double* beta0, double* out, size_t out_stride, int T, cudaStream_t st);
+size_t chase_workspace(const Plan* pl, int T);
+int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e, int T, cudaStream_t st);
+int band_solve_launch(const Plan* pl, const double* bandS, double* Lg, const double* gu, double* Bq, int ldb, int nz,
+                      double* x, double* noise, double* z_low, double* z_high, size_t out_stride, int T,
                       cudaStream_t st);
 int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes);
 int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,

@@ -151,6 +151,30 @@ int chd_gamma_band(const chd_plan* plan, int B, const double* band, const double
                    int T, const double* gamma_grid, int gamma_min_mode, double gamma_min_base, double* gamma_min,
                    double* x, double* noise, double* z_low, double* z_high, double* gamma, double* lambda_min,
                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* Two-stage reduction building blocks (inspection / test entry points -- chd_regress and
+ * chd_prune_chain run the same kernels when the plan is in two-stage mode).  Replace, together, the eigh of
+ * interpolatory.py:48.  CHD_BAND = 32 is the half-width of the band form; band arrays are T x n x CHD_BAND_LD with
+ * band[t][i][d] = T_b(i, i-d), d = 0..CHD_BAND.
+ *   chd_band_reduce         K (T x n x ldk, lower triangle read, destroyed: holds the block reflectors afterwards),
+ *                           ga (T x n), B (T x n x ldb or NULL: B <- Q^T B)  ->  band, beta0 (T): Q^T ga = beta0 e_0
+ *   chd_band_backtransform  out (T x n) = -beta0 Q x, with K / workspace as left by chd_band_reduce
+ *   chd_band_chase          band -> tridiagonal d, e (T x n each, e[n-1] = 0), values only (bulge chasing)
+ *   chd_band_solve          x = (T_b + gamma_used I)^-1 e_0, noise, and the Z-test bounds from Bq = Q^T S */
+#define CHD_BAND 32
+#define CHD_BAND_LD 34
+size_t chd_band_workspace_bytes(const chd_plan* plan, int T);
+int chd_band_reduce(const chd_plan* plan, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nb_cols,
+                    double* band, double* beta0, void* workspace, size_t workspace_bytes, void* stream);
+int chd_band_backtransform(const chd_plan* plan, const double* K, int ldk, const double* x, const double* beta0,
+                           double* out, int T, void* workspace, size_t workspace_bytes, void* stream);
+int chd_band_chase(const chd_plan* plan, const double* band, int T, double* d, double* e, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int chd_band_solve(const chd_plan* plan, const double* band, const double* gamma_used, double* Bq, int ldb, int nz,
+                   int T, double* x, double* noise, double* z_low, double* z_high, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* Selects the regression path of chd_regress / chd_prune_chain: 1 = two-stage (default), 0 = one-stage
+ * Householder tridiagonalisation (chd_tridiag).  Workspace sizes depend on it: call before chd_workspace_bytes. */
+int chd_plan_set_two_stage(chd_plan* plan, int on);
 /* Optional timing of the dominant kernel: when enabled, every tridiagonalisation launch is bracketed by
  * cudaEvents on its own stream; chd_profile_read synchronises those events and returns the summed duration
  * (ms) and the number of launches since the last chd_profile_enable(1). */
