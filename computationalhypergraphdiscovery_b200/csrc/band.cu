@@ -281,6 +281,192 @@ __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(QrArgs a) {
   if (CS > 1) cluster.sync();   // no CTA may exit while its shared memory can still be written remotely
 }
 
+// ------------------------------------------------------------------ panel QR, register-resident variant
+// One thread per panel row (the row's NB values live in registers), RG_THREADS rows per CTA, clusters of up to 16
+// CTAs.  Per column ONE cluster-wide exchange: the unscaled products  u[c] = sum_{r > tc} x_r P[r][c]  (x = column
+// tc) for all NB columns at once -- u[tc] is the squared norm the reflector needs, u[c > tc] gives v^T P, u[c < tc]
+// gives the Gram entries v_c . v_tc of the compact-WY factor -- together with row tc itself (from its owner).  The
+// row sums over the 32 rows of a warp use a transposing butterfly (31 shuffles for 32 columns).
+constexpr int RG_THREADS = 512;
+constexpr int RG_NW = RG_THREADS / 32;
+constexpr int RG_XW = 2 * NB;
+
+template <int TC>
+struct RgCol {
+  // processes column TC and recurses (compile-time column index: the row stays in registers)
+  template <typename Ex>
+  static __device__ __forceinline__ void run(double (&P)[NB], int pr, bool valid, int nref, int lane, int wid, double* red,
+                                             double* mine, const double* tot, double* Gs, double* taus, Ex& exchange) {
+    if (TC < nref) {
+      const double x = (valid && pr > TC) ? P[TC] : 0.0;
+      // ---- transposing butterfly: lane c ends up with sum over the warp's rows of x * P[c]
+      double t16[16], t8[8], t4[4], t2[2], t1;
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const double a0 = x * P[c], a1 = x * P[c + 16];
+          const double keep = hi ? a1 : a0, send = hi ? a0 : a1;
+          t16[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const double keep = hi ? t16[c + 8] : t16[c], send = hi ? t16[c] : t16[c + 8];
+          t8[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double keep = hi ? t8[c + 4] : t8[c], send = hi ? t8[c] : t8[c + 4];
+          t4[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+      }
+      {
+        const bool hi = lane & 2;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const double keep = hi ? t4[c + 2] : t4[c], send = hi ? t4[c] : t4[c + 2];
+          t2[c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      }
+      {
+        const bool hi = lane & 1;
+        const double keep = hi ? t2[1] : t2[0], send = hi ? t2[0] : t2[1];
+        t1 = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      red[wid * NB + lane] = t1;
+      if (wid == 1) mine[NB + lane] = 0.0;        // row TC: zero unless this CTA owns it (owner overwrites below)
+      __syncthreads();
+      if (wid == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < RG_NW; ++w) s += red[w * NB + lane];
+        mine[lane] = s;
+      }
+      if (valid && pr == TC) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) mine[NB + c] = P[c];
+      }
+      exchange();
+      const double ssq = tot[TC], alpha = tot[NB + TC];
+      double beta, tau, scale;
+      if (ssq == 0.0) {
+        beta = alpha; tau = 0.0; scale = 0.0;
+      } else {
+        beta = -copysign(sqrt(alpha * alpha + ssq), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
+      }
+      const double v = (!valid || pr < TC) ? 0.0 : ((pr == TC) ? 1.0 : x * scale);
+      const double tv = tau * v;
+#pragma unroll
+      for (int c = TC + 1; c < NB; ++c) P[c] = fma(-tv, fma(scale, tot[c], tot[NB + c]), P[c]);
+      if (valid && pr >= TC) P[TC] = (pr == TC) ? beta : v;
+      if (wid == 0) {
+        if (lane < TC) Gs[lane * QR_S + TC] = fma(scale, tot[lane], tot[NB + lane]);
+        if (lane == 0) taus[TC] = tau;
+      }
+      __syncthreads();   // tot[] consumed before the next exchange overwrites it
+      RgCol<TC + 1>::run(P, pr, valid, nref, lane, wid, red, mine, tot, Gs, taus, exchange);
+    }
+  }
+};
+template <>
+struct RgCol<NB> {
+  template <typename Ex>
+  static __device__ __forceinline__ void run(double (&)[NB], int, bool, int, int, int, double*, double*, const double*,
+                                             double*, double*, Ex&) {}
+};
+
+__global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
+  __shared__ __align__(16) double xch[2 * QR_MAXCS * RG_XW];
+  __shared__ double red[RG_NW * NB];
+  __shared__ double mine[RG_XW];
+  __shared__ double tot[RG_XW];
+  __shared__ double taus[NB];
+  __shared__ double Gs[NB * QR_S];
+  __shared__ double Ts[NB * QR_S];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int g = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = a.n, r0 = a.r0, c0 = a.c0, ldk = a.ldk;
+  const int m = n - r0;
+  const int nref = min(NB, m - 1);
+  double* A = a.A + (size_t)t * a.strideA;
+  const int pr = g * a.RP + tid;
+  const bool valid = (tid < a.RP) && (pr < m);
+  double* rowg = A + (size_t)(r0 + (valid ? pr : 0)) * ldk + c0;
+
+  double P[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) {
+    double2 v2 = make_double2(0.0, 0.0);
+    if (valid) v2 = *reinterpret_cast<const double2*>(rowg + c);
+    P[c] = v2.x; P[c + 1] = v2.y;
+  }
+  for (int e = tid; e < NB * QR_S; e += RG_THREADS) { Gs[e] = 0.0; Ts[e] = 0.0; }
+  if (tid < NB) taus[tid] = 0.0;
+
+  int par = 0;
+  auto exchange = [&]() {
+    __syncthreads();
+    if (CS == 1) {
+      if (tid < RG_XW) tot[tid] = mine[tid];
+    } else {
+      for (int e = tid; e < CS * RG_XW; e += RG_THREADS) {
+        const int dst = e / RG_XW, q = e % RG_XW;
+        double* remote = cluster.map_shared_rank(xch + (par * QR_MAXCS + g) * RG_XW, dst);
+        remote[q] = mine[q];
+      }
+      cluster.sync();
+      if (tid < RG_XW) {
+        double s = 0.0;
+        for (int q = 0; q < CS; ++q) s += xch[(par * QR_MAXCS + q) * RG_XW + tid];
+        tot[tid] = s;
+      }
+      par ^= 1;
+    }
+    __syncthreads();
+  };
+  __syncthreads();
+  RgCol<0>::run(P, pr, valid, nref, lane, wid, red, mine, tot, Gs, taus, exchange);
+
+  // ---- compact-WY factor (dlarft, forward columnwise): lane a owns row a of T
+  if (wid == 0 && g == 0) {
+    double Tr[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) Tr[k] = 0.0;
+#pragma unroll
+    for (int tc = 0; tc < NB; ++tc) {
+      const double tau = taus[tc];
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < tc; ++k) s = fma(Tr[k], Gs[k * QR_S + tc], s);   // Tr[k] == 0 for k < lane
+      Tr[tc] = (lane < tc) ? -tau * s : ((lane == tc) ? tau : 0.0);
+    }
+    double* Tf = a.Tf + (size_t)t * a.tf_stride;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) Tf[lane * NB + k] = Tr[k];
+  }
+  // ---- outputs: the factored block in place (R over V), V as a dense operand
+  if (valid) {
+    double* V = a.V + (size_t)t * n * NB + (size_t)(r0 + pr) * NB;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) {
+      *reinterpret_cast<double2*>(rowg + c) = make_double2(P[c], P[c + 1]);
+      const double v0 = (c >= nref || pr < c) ? 0.0 : ((pr == c) ? 1.0 : P[c]);
+      const double v1 = (c + 1 >= nref || pr < c + 1) ? 0.0 : ((pr == c + 1) ? 1.0 : P[c + 1]);
+      *reinterpret_cast<double2*>(V + c) = make_double2(v0, v1);
+    }
+  }
+  if (CS > 1) cluster.sync();
+}
+
 // ------------------------------------------------------------------ Y = A22 V
 constexpr int SY_BM = 128, SY_KC = 32;
 constexpr int SY_SD = SY_KC + 4;    // direct tile [i][k] stride (== 4 mod 8: conflict-free fragment loads)
@@ -489,9 +675,9 @@ constexpr size_t WF_SMEM = (3 * NB * (NB + 1) + NB * SY_ZW + 2 * WF_BM * (NB + 1
 __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
   extern __shared__ __align__(16) double smem[];
   double* Ts = smem;                        // NB x (NB + 1)
-  double* TM = Ts + NB * (NB + 1);          // T^T M
-  double* Ms = TM + NB * (NB + 1);
-  double* TZ = Ms + NB * (NB + 1);          // NB x SY_ZW
+  double* TM = Ts + NB * (NB + 1);          // M, then T^T M
+  double* Ms = TM + NB * (NB + 1);          // (unused half kept for layout compatibility)
+  double* TZ = Ms + NB * (NB + 1);          // NB x SY_ZW: V^T B, then T^T V^T B
   double* Vs = TZ + NB * SY_ZW;             // WF_BM x (NB + 1)
   double* Xs = Vs + WF_BM * (NB + 1);
   const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -503,7 +689,11 @@ __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
   const bool hz = a.Bq && a.nz > 0;
   for (int e = tid; e < NB * NB; e += 256) {
     Ts[(e / NB) * (NB + 1) + (e % NB)] = Tf[e];
-    Ms[(e / NB) * (NB + 1) + (e % NB)] = a.Mred[(size_t)t * NB * NB + e];
+    TM[(e / NB) * (NB + 1) + (e % NB)] = a.Mred[(size_t)t * NB * NB + e];
+  }
+  if (hz) {
+    const double* Zr = a.Zred + (size_t)t * NB * SY_ZW;
+    for (int e = tid; e < NB * SY_ZW; e += 256) TZ[e] = Zr[e];
   }
   for (int e = tid; e < WF_BM * NB; e += 256) {
     const int rl = e / NB, c = e % NB;
@@ -512,25 +702,37 @@ __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
     Xs[rl * (NB + 1) + c] = ok ? Y[(size_t)(i0 + rl) * NB + c] : 0.0;
   }
   __syncthreads();
-  // TM[a][c] = sum_{k <= a} T[k][a] M[k][c]
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int ar = e / NB, c = e % NB;
-    double s = 0.0;
-    for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], Ms[k * (NB + 1) + c], s);
-    TM[ar * (NB + 1) + c] = s;
-  }
-  if (hz) {
-    // TZ[a][z] = sum_{k <= a} T[k][a] Zred[k][z]
-    const double* Zr = a.Zred + (size_t)t * NB * SY_ZW;
-    for (int e = tid; e < NB * SY_ZW; e += 256) {
-      const int ar = e / SY_ZW, z = e % SY_ZW;
+  // T^T M and T^T (V^T B) in registers, then in place:  out[a][c] = sum_{k <= a} T[k][a] in[k][c]
+  double tm[4], tz[16];
+  {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int ar = wid + 8 * u;
       double s = 0.0;
-      for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], Zr[k * SY_ZW + z], s);
-      TZ[e] = s;
+      for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], TM[k * (NB + 1) + lane], s);
+      tm[u] = s;
+    }
+    if (hz) {
+      const int z = tid & 127, hg = tid >> 7;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int ar = hg + 2 * u;
+        double s = 0.0;
+        for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], TZ[k * SY_ZW + z], s);
+        tz[u] = s;
+      }
     }
   }
   __syncthreads();
-  // X1 = Y - 1/2 V TM   (in place in Xs; each thread owns whole elements, rows wid + 8 q)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) TM[(wid + 8 * u) * (NB + 1) + lane] = tm[u];
+  if (hz) {
+    const int z = tid & 127, hg = tid >> 7;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) TZ[(hg + 2 * u) * SY_ZW + z] = tz[u];
+  }
+  __syncthreads();
+  // X1 = Y - 1/2 V TM   (rows wid + 8 q)
   double x1[WF_BM / 8];
 #pragma unroll
   for (int q = 0; q < WF_BM / 8; ++q) {
@@ -556,11 +758,22 @@ __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
     double* Bq = a.Bq + (size_t)t * n * a.ldb;
     const int z = tid & 127, hg = tid >> 7;
     if (z < a.nz) {
-      for (int rl = hg; rl < WF_BM && i0 + rl < n; rl += 2) {
-        double s = 0.0;
+      // batches of 8 rows: all loads in flight before the first store
+      for (int rb = 0; rb < WF_BM; rb += 16) {
+        double bv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + rb + hg + 2 * u;
+          bv[u] = (i < n) ? Bq[(size_t)i * a.ldb + z] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rl = rb + hg + 2 * u;
+          double s = 0.0;
 #pragma unroll 8
-        for (int k = 0; k < NB; ++k) s = fma(Vs[rl * (NB + 1) + k], TZ[k * SY_ZW + z], s);
-        Bq[(size_t)(i0 + rl) * a.ldb + z] -= s;
+          for (int k = 0; k < NB; ++k) s = fma(Vs[rl * (NB + 1) + k], TZ[k * SY_ZW + z], s);
+          if (i0 + rl < n) Bq[(size_t)(i0 + rl) * a.ldb + z] = bv[u] - s;
+        }
       }
     }
   }
@@ -913,9 +1126,30 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
     CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
     CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
     CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CHD_CUDA(cudaFuncSetAttribute(backtransform2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pl->smem_optin));
     attr_set = true;
+  }
+  // largest cluster the register-resident panel QR may use: 16 (non-portable) when the device can co-schedule it
+  static int reg_max_cs = -1;
+  {
+    const char* e = getenv("CHD_QR_REG");     // tuning / test switch: 0 disables the register-resident kernel
+    if (e && atoi(e) == 0) reg_max_cs = 0;
+    else if (reg_max_cs <= 0) {
+      reg_max_cs = 8;
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cfg.gridDim = dim3(16, 1); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = 0;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, panel_qr_reg_kernel, &cfg) == cudaSuccess && nclusters > 0)
+        reg_max_cs = 16;
+      else
+        (void)cudaGetLastError();
+    }
   }
   const size_t strideA = (size_t)n * ldk;
   if (ldk > n) {
@@ -938,17 +1172,29 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
     a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Tf = bb.Tf + (size_t)p * NB * NB;
     a.tf_stride = bb.tf_stride; a.n = n; a.r0 = r0; a.c0 = c0;
     size_t smem;
-    const int cs = qr_cluster_size(pl, m, a.RP, a.RS, smem);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cs, T);
-    cfg.blockDim = dim3(QR_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_kernel, a));
+    cfg.stream = st;
+    int rcs = 1;
+    while (rcs < reg_max_cs && (m + rcs - 1) / rcs > RG_THREADS) rcs *= 2;
+    if (reg_max_cs > 0 && (m + rcs - 1) / rcs <= RG_THREADS) {
+      a.RP = (m + rcs - 1) / rcs; a.RS = 0;
+      cfg.gridDim = dim3(rcs, T);
+      cfg.blockDim = dim3(RG_THREADS);
+      cfg.dynamicSmemBytes = 0;
+      at[0].val.clusterDim.x = rcs;
+      CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_reg_kernel, a));
+    } else {
+      const int cs = qr_cluster_size(pl, m, a.RP, a.RS, smem);
+      cfg.gridDim = dim3(cs, T);
+      cfg.blockDim = dim3(QR_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      at[0].val.clusterDim.x = cs;
+      CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_kernel, a));
+    }
     g_launches.fetch_add(1);
     if ((rc = trailing_launch(pl, K, ldk, T, B, ldb, nz, r0, p, bb, st))) return rc;
   }

@@ -85,16 +85,27 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
       if (lane < len) __stcg(bw + (size_t)(lo + lane) * CLD + (lane + 1), (lane == 0) ? beta : 0.0);
     }
     while (true) {
+      // ---------------- all loads of the hop up front (64 independent requests per lane in flight)
+      const int lo2 = hi + 1, hi2 = min(hi + CB, n - 1);
+      const int len2 = hi2 - lo2 + 1;
+      const int off = lo2 - lo;   // == len
+      double dr[CB], sr[CB];
+#pragma unroll
+      for (int l = 0; l < CB; ++l)   // row l of D, lanes = d (column l - d)
+        dr[l] = (l < len && lane <= l) ? __ldcg(bw + (size_t)(lo + l) * CLD + lane) : 0.0;
+#pragma unroll
+      for (int l = 0; l < CB; ++l)   // row l of S, lanes = column c: A(lo2+l, lo+c) at d = off + l - c
+        sr[l] = (l < len2 && lane < len) ? __ldcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane)) : 0.0;
       // ---------------- diagonal block D = A[lo..hi, lo..hi]  <- H D H
+#pragma unroll
       for (int l = 0; l < CB; ++l) {
-        // row l, lanes = d (column l - d)
-        double x = 0.0;
-        if (l < len && lane <= l) x = __ldcg(bw + (size_t)(lo + l) * CLD + lane);
         if (lane <= l) {
-          D[l * CS_ + (l - lane)] = x;
-          D[(l - lane) * CS_ + l] = x;
+          D[l * CS_ + (l - lane)] = dr[l];
+          D[(l - lane) * CS_ + l] = dr[l];
         }
       }
+#pragma unroll
+      for (int l = 0; l < CB; ++l) S[l * CS_ + lane] = sr[l];
       vs[lane] = v;
       __syncwarp();
       double p = 0.0;
@@ -111,19 +122,9 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
       for (int l = 0; l < len; ++l)
         if (lane <= l) __stcg(bw + (size_t)(lo + l) * CLD + lane, D[l * CS_ + (l - lane)]);
       // ---------------- block below: S = A[lo2..hi2, lo..hi]  <- S H, then the next reflector from its first column
-      const int lo2 = hi + 1, hi2 = min(hi + CB, n - 1);
-      const int len2 = hi2 - lo2 + 1;
       bool last = (len2 <= 0);
       double v2 = 0.0, tau2 = 0.0;
       if (!last) {
-        const int off = lo2 - lo;   // == len
-        for (int l = 0; l < CB; ++l) {
-          // row l of S, lanes = column c: A(lo2+l, lo+c) at d = off + l - c
-          double x = 0.0;
-          if (l < len2 && lane < len) x = __ldcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane));
-          S[l * CS_ + lane] = x;
-        }
-        __syncwarp();
         double u = 0.0;
 #pragma unroll 8
         for (int c = 0; c < CB; ++c) u = fma(S[lane * CS_ + c], vs[c], u);
