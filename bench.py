@@ -232,7 +232,9 @@ def run_b200(args):
     X, _names = make_data(n, N, seed=0)
     X = np.ascontiguousarray((X - X.mean(0)) / X.std(0))
     plan = _native.Plan(n, N, N)
-    Tb = args.targets or plan.matrices_per_wave
+    # two-stage path: every launch is batched over the targets in flight (16 per kernel state: 8.6 GB of work
+    # matrices at n = 8192); one-stage path: one cooperative wave
+    Tb = args.targets or (min(16, max(1, N)) if plan.two_stage else plan.matrices_per_wave)
     Xd = torch.from_numpy(X).to(dev)
     cl = torch.arange(N, dtype=torch.int32, device=dev)
     descs = {"linear": _native.make_desc(0, 2.0), "quadratic": _native.make_desc(1, 1.0, alpha=1.0),
@@ -273,6 +275,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    prof = {}
+
     def timed(fn, warmup, steps, sample_clocks=False):
         for _ in range(warmup):
             fn()
@@ -290,6 +294,8 @@ def run_b200(args):
         barrier()
         ms = e0.elapsed_time(e1)
         tri_ms, tri_launches = _native.profile_read()
+        prof.clear()
+        prof.update(_native.profile_read_all())
         _native.profile_enable(False)
         launches = _native.launch_count() - l0
         clocks = sampler.stop() if sampler else None
@@ -312,14 +318,8 @@ def run_b200(args):
     total_steps = nkm * Tb * world * args.steps
     value = total_steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (batched tridiagonalisation), timed with events around each launch
-    # one tridiagonalisation = a few cooperative launches (multi-level restart x waves); all of them are bracketed
-    # by CUDA events inside the library.  achieved = credited flops of all matrices reduced in the timed region
-    # / summed duration of those launches.
+    # ---- roofline of the dominant kernel, timed live with CUDA events around every launch inside the timed region
     n_mats = nkm * Tb * args.steps
-    mats_per_launch = n_mats / max(tri_launches, 1)
-    dur = tri_ms * 1e-3 / max(tri_launches, 1)
-    achieved_tf = credited_flops_tridiag(n) * n_mats / (tri_ms * 1e-3) / 1e12
     peak_tf = _native.dmma_peak_tflops(20000) if rank == 0 else 0.0
     peaks = {}
     try:
@@ -327,28 +327,78 @@ def run_b200(args):
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "tridiag_traffic.json")))
-        per_matrix = tr.get(f"n{n}_per_matrix")
-        traffic = per_matrix * mats_per_launch if per_matrix else None
-    except Exception:  # noqa: BLE001
-        pass
-    # bytes the one-stage reduction must stream: lower triangle of the trailing matrix once per column (symv,
-    # 4n^3/3 B) + read/write of it once per panel (8n^3/(3 nb) B)
-    alg_bytes = (4.0 * n ** 3 / 3.0 + 8.0 * n ** 3 / (3.0 * plan.panel_width)) * mats_per_launch
-    roofline = {"kernel": "tridiag_kernel (batched Householder tridiagonalisation, DMMA trailing update)",
-                "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                "peak_source": "FP64 DMMA m8n8k4 issue-rate probe run in this process (chd_dmma_peak); "
-                               "MEASURED_PEAKS.json has no FP64 figure",
-                "flops_per_launch": credited_flops_tridiag(n) * mats_per_launch,
-                "avg_launch_ms": dur * 1e3, "launches_timed": tri_launches,
-                "share_of_step": tri_ms / ms,
-                "hbm_view": {"bound": "hbm", "achieved": alg_bytes / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes / dur / 1e9 / hbm_peak,
-                             "note": "one-stage reduction streams the lower triangle of the trailing matrix once per "
-                                     "column (4n^3/3 B) plus one read+write per panel (8n^3/(3 nb) B)"}}
+    peak_src = ("FP64 DMMA m8n8k4 issue-rate probe run in this process (chd_dmma_peak); MEASURED_PEAKS.json has no "
+                "FP64 figure")
+    prof_main = dict(prof)
+    if plan.two_stage:
+        # Stage 1 (dense -> band, NB = 32) is two DMMA GEMM kernels per panel, batched over the targets in flight:
+        #   symm  Y = A22 V          2 m^2 NB flop per matrix and panel  (sum over panels: 2/3 n^3)
+        #   syr2k A22 -= VW^T+WV^T   2 m^2 NB flop (lower triangle only)  (sum over panels: 2/3 n^3)
+        NBW = _native.BAND
+        ms_list = [n - p * NBW for p in range(0, (n - 2) // NBW + 1) if n - p * NBW >= 2]
+        ms_list = [n] + [m for m in ms_list[1:]]          # panel 0 is H_{-1} on the full matrix
+        gemm_flops = sum(2.0 * m * m * NBW for m in ms_list)   # per kernel, per matrix
+        kern_stats = {}
+        for kname in ("symm", "syr2k", "panel_qr", "wform", "chase", "band_solve", "backtransform"):
+            if kname in prof_main:
+                kms, kcnt = prof_main[kname]
+                kern_stats[kname] = {"ms": kms, "launches": kcnt, "share_of_step": kms / ms}
+        dom = max(("symm", "syr2k"), key=lambda k: prof_main.get(k, (0.0, 0))[0])
+        dms, dcnt = prof_main.get(dom, (0.0, 1))
+        achieved_tf = gemm_flops * n_mats / (dms * 1e-3) / 1e12 if dms else 0.0
+        # algorithmic bytes: symm reads the lower triangle twice (tile + its transpose), syr2k reads + writes it once
+        alg_bytes = sum(8.0 * m * m for m in ms_list) * n_mats
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "stage1_traffic.json")))
+            per_matrix = tr.get(f"{dom}_n{n}_per_matrix")
+            traffic = per_matrix * n_mats / max(dcnt, 1) if per_matrix else None
+        except Exception:  # noqa: BLE001
+            pass
+        stage1_ms = sum(prof_main.get(k, (0.0, 0))[0] for k in ("symm", "syr2k", "panel_qr", "wform"))
+        roofline = {"kernel": f"{dom}_kernel (dense->band stage of the two-stage reduction, FP64 DMMA m8n8k4, "
+                              f"batched over {Tb} targets per launch)",
+                    "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peak_src,
+                    "flops_per_launch": gemm_flops * n_mats / max(dcnt, 1),
+                    "avg_launch_ms": dms / max(dcnt, 1), "launches_timed": dcnt, "share_of_step": dms / ms,
+                    "stage1": {"credited_flops_per_matrix": credited_flops_tridiag(n),
+                               "achieved_tflops": credited_flops_tridiag(n) * n_mats / (stage1_ms * 1e-3) / 1e12
+                               if stage1_ms else None,
+                               "frac_of_dmma_peak": (credited_flops_tridiag(n) * n_mats / (stage1_ms * 1e-3) / 1e12 /
+                                                     peak_tf) if stage1_ms and peak_tf else None,
+                               "ms_per_matrix": stage1_ms / n_mats,
+                               "note": "symm + syr2k + panel QR + W formation, credited 4/3 n^3 (SURVEY 8d)"},
+                    "kernels": kern_stats,
+                    "hbm_view": {"bound": "hbm", "achieved": alg_bytes / (dms * 1e-3) / 1e9 if dms else None,
+                                 "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_bytes / (dms * 1e-3) / 1e9 / hbm_peak if dms else None,
+                                 "note": "8 m^2 B per panel and matrix for either GEMM kernel (symm: lower triangle "
+                                         "read as tile and as transposed tile; syr2k: read + write)"}}
+    else:
+        mats_per_launch = n_mats / max(tri_launches, 1)
+        dur = tri_ms * 1e-3 / max(tri_launches, 1)
+        achieved_tf = credited_flops_tridiag(n) * n_mats / (tri_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "tridiag_traffic.json")))
+            per_matrix = tr.get(f"n{n}_per_matrix")
+            traffic = per_matrix * mats_per_launch if per_matrix else None
+        except Exception:  # noqa: BLE001
+            pass
+        # bytes the one-stage reduction must stream: lower triangle of the trailing matrix once per column (symv,
+        # 4n^3/3 B) + read/write of it once per panel (8n^3/(3 nb) B)
+        alg_bytes = (4.0 * n ** 3 / 3.0 + 8.0 * n ** 3 / (3.0 * plan.panel_width)) * mats_per_launch
+        roofline = {"kernel": "tridiag_kernel (batched Householder tridiagonalisation, DMMA trailing update)",
+                    "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peak_src,
+                    "flops_per_launch": credited_flops_tridiag(n) * mats_per_launch,
+                    "avg_launch_ms": dur * 1e3, "launches_timed": tri_launches,
+                    "share_of_step": tri_ms / ms,
+                    "hbm_view": {"bound": "hbm", "achieved": alg_bytes / dur / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_bytes / dur / 1e9 / hbm_peak,
+                                 "note": "one-stage reduction streams the lower triangle of the trailing matrix once "
+                                         "per column (4n^3/3 B) plus one read+write per panel (8n^3/(3 nb) B)"}}
 
     # ---- end to end through the public call with HOST buffers (pinned), H2D + D2H inside the timed region
     sts2 = [setup_state(k) for k in knames]
@@ -395,7 +445,8 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": counters["h2d"],
                         "d2h_bytes_per_step": counters["d2h"]},
                 "roofline": roofline, "per_kernel": per_kernel,
-                "plan": {"ctas_per_matrix": plan.ctas_per_matrix, "matrices_per_wave": plan.matrices_per_wave,
+                "plan": {"two_stage": plan.two_stage, "band_half_width": _native.BAND,
+                         "ctas_per_matrix": plan.ctas_per_matrix, "matrices_per_wave": plan.matrices_per_wave,
                          "panel_width": plan.panel_width, "threads_per_cta": plan.threads_per_cta,
                          "bulk_symv": plan.bulk_symv}}
         if world == 1 and not args.no_cpu_baseline:

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "chd_predict": (_i, [_vp, ctypes.POINTER(KernelDesc), _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "chd_tridiag": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "chd_dmma_peak": (_i, [_i, ctypes.POINTER(_d)]),
+    "chd_fp64_probe": (_i, [_i, _i, ctypes.POINTER(_d)]),
     "chd_gamma_band": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                             _vp, _sz, _vp]),
     "chd_band_workspace_bytes": (_sz, [_vp, _i]),
@@ -63,6 +64,8 @@ _SIGNATURES = {
     "chd_plan_set_two_stage": (_i, [_vp, _i]),
     "chd_profile_enable": (_i, [_i]),
     "chd_profile_read": (_i, [ctypes.POINTER(_d), ctypes.POINTER(_i)]),
+    "chd_profile_read_cat": (_i, [_i, ctypes.POINTER(_d), ctypes.POINTER(_i)]),
+    "chd_plan_two_stage": (_i, [_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -136,6 +139,7 @@ class Plan:
         self.ctas_per_matrix, self.matrices_per_wave, self.sm_count = g.value, w.value, s.value
         _check(lib.chd_plan_tuning(h, ctypes.byref(g), ctypes.byref(w), ctypes.byref(s)), "chd_plan_tuning")
         self.panel_width, self.threads_per_cta, self.bulk_symv = g.value, w.value, s.value
+        self.two_stage = bool(lib.chd_plan_two_stage(h))
         self.ldk = (self.n + 1) // 2 * 2
         self.grid = torch.from_numpy(gamma_grid_host()).to(self.device)
         self._ws = None
@@ -222,6 +226,7 @@ class Plan:
     # ---- two-stage building blocks
     def set_two_stage(self, on):
         _check(load().chd_plan_set_two_stage(self._h, int(bool(on))), "chd_plan_set_two_stage")
+        self.two_stage = bool(on)
         self._ws = None
 
     def band_workspace(self, T):
@@ -343,7 +348,29 @@ def profile_read():
     return ms.value, cnt.value
 
 
+PROFILE_CATEGORIES = {"tridiag": 0, "symm": 1, "syr2k": 2, "panel_qr": 3, "chase": 4, "wform": 5, "band_solve": 6,
+                      "backtransform": 7}
+
+
+def profile_read_all():
+    """{kernel: (total ms, launches)} of the regression kernels since profile_enable(True)."""
+    out = {}
+    for name, cat in PROFILE_CATEGORIES.items():
+        ms, cnt = ctypes.c_double(), ctypes.c_int()
+        _check(load().chd_profile_read_cat(cat, ctypes.byref(ms), ctypes.byref(cnt)), "chd_profile_read_cat")
+        if cnt.value:
+            out[name] = (ms.value, cnt.value)
+    return out
+
+
 def dmma_peak_tflops(iters=20000):
     v = ctypes.c_double()
     _check(load().chd_dmma_peak(int(iters), ctypes.byref(v)), "chd_dmma_peak")
+    return v.value
+
+
+def fp64_probe_tflops(mode, iters=20000):
+    """mode 0: DMMA only, 1: DFMA only, 2: both interleaved."""
+    v = ctypes.c_double()
+    _check(load().chd_fp64_probe(int(iters), int(mode), ctypes.byref(v)), "chd_fp64_probe")
     return v.value

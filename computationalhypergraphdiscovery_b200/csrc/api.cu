@@ -42,12 +42,11 @@ static size_t regress_workspace(const Plan* pl, int T) {
   b += 5 * align_up(T * n * sizeof(double), 256);
   b += align_up(T * sizeof(double), 256);
   b += align_up((size_t)T * CHD_GRID_POINTS * sizeof(double), 256);
-  if (pl->two_stage) {
-    b += band_workspace(pl, T) + chase_workspace(pl, T);
-    b += align_up((size_t)T * n * CHD_BAND_LD * sizeof(double), 256) + align_up(T * sizeof(double), 256);
-    return b + 4096;
-  }
-  return b + tridiag_workspace(pl, T) + 4096;
+  // sized for either path (chd_plan_set_two_stage / chd_tridiag may be used on the same workspace)
+  size_t two = band_workspace(pl, T) + chase_workspace(pl, T) +
+               align_up((size_t)T * n * CHD_BAND_LD * sizeof(double), 256) + align_up(T * sizeof(double), 256);
+  size_t one = tridiag_workspace(pl, T);
+  return b + (two > one ? two : one) + 8192;
 }
 
 static bool regress_carve(const Plan* pl, int T, Carver& cv, RegressBuffers& rb) {
@@ -126,6 +125,36 @@ __global__ void dmma_peak_kernel(int iters, double* sink) {
   if (s == 123.456) sink[0] = s;
 }
 
+// mode 0: DMMA only, 1: DFMA only, 2: both interleaved (8 DFMA per DMMA = equal flops): do the FP64 tensor and the
+// FP64 vector pipes add up?
+__global__ void fp64_mix_kernel(int iters, int mode, double* sink) {
+  double c[8][2];
+  double f[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = threadIdx.x * 1e-3 + i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+    if (mode != 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    if (mode != 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fma(f[i], a, b);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += f[i];
+  if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace chd
 
 using namespace chd;
@@ -148,7 +177,7 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
   pl->smem_optin = prop.sharedMemPerBlockOptin;
   pl->nb = 32;
   pl->rows_per_chunk = 16;
-  pl->two_stage = getenv("CHD_TWO_STAGE") ? atoi(getenv("CHD_TWO_STAGE")) : 0;
+  pl->two_stage = getenv("CHD_TWO_STAGE") ? atoi(getenv("CHD_TWO_STAGE")) : 1;
   int G = ctas_per_matrix;
   if (G <= 0) {
     if (n <= 256) G = 2;
@@ -439,6 +468,40 @@ extern "C" int chd_plan_set_two_stage(chd_plan* plan, int on) {
 
 extern "C" int chd_profile_enable(int on) { return profile_enable(on); }
 extern "C" int chd_profile_read(double* total_ms, int* launches) { return profile_read(total_ms, launches); }
+extern "C" int chd_profile_read_cat(int category, double* total_ms, int* launches) {
+  return profile_read_cat(category, total_ms, launches);
+}
+extern "C" int chd_plan_two_stage(const chd_plan* plan) { return plan ? ((const Plan*)plan)->two_stage : -1; }
+
+extern "C" int chd_fp64_probe(int iters, int mode, double* tflops) {
+  if (iters <= 0 || !tflops) return CHD_EINVAL;
+  int dev = 0;
+  CHD_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CHD_CUDA(cudaGetDeviceProperties(&prop, dev));
+  double* sink;
+  CHD_CUDA(cudaMalloc(&sink, 8));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256;
+  fp64_mix_kernel<<<blocks, threads>>>(iters / 10 + 1, mode, sink);
+  cudaEvent_t e0, e1;
+  CHD_CUDA(cudaEventCreate(&e0));
+  CHD_CUDA(cudaEventCreate(&e1));
+  CHD_CUDA(cudaEventRecord(e0));
+  fp64_mix_kernel<<<blocks, threads>>>(iters, mode, sink);
+  CHD_CUDA(cudaEventRecord(e1));
+  CHD_CUDA(cudaEventSynchronize(e1));
+  g_launches.fetch_add(2);
+  float ms = 0;
+  CHD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  double per_iter = 0.0;
+  if (mode != 1) per_iter += 8.0 * 512.0;
+  if (mode != 0) per_iter += 64.0 * 64.0;
+  *tflops = (double)blocks * (threads / 32) * (double)iters * per_iter / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return CHD_OK;
+}
 
 extern "C" int chd_dmma_peak(int iters, double* tflops) {
   if (iters <= 0 || !tflops) return CHD_EINVAL;

@@ -291,15 +291,65 @@ constexpr int RG_THREADS = 512;
 constexpr int RG_NW = RG_THREADS / 32;
 constexpr int RG_XW = 2 * NB;
 
-template <int TC>
-struct RgCol {
-  // processes column TC and recurses (compile-time column index: the row stays in registers)
-  template <typename Ex>
-  static __device__ __forceinline__ void run(double (&P)[NB], int pr, bool valid, int nref, int lane, int wid, double* red,
-                                             double* mine, const double* tot, double* Gs, double* taus, Ex& exchange) {
-    if (TC < nref) {
-      const double x = (valid && pr > TC) ? P[TC] : 0.0;
-      // ---- transposing butterfly: lane c ends up with sum over the warp's rows of x * P[c]
+__global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
+  __shared__ __align__(16) double xch[2 * QR_MAXCS * RG_XW];
+  __shared__ double red[RG_NW * NB];
+  __shared__ double mine[RG_XW];
+  __shared__ double tot[RG_XW];
+  __shared__ double taus[NB];
+  __shared__ double Gs[NB * QR_S];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int g = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = a.n, r0 = a.r0, c0 = a.c0, ldk = a.ldk;
+  const int m = n - r0;
+  const int nref = min(NB, m - 1);
+  double* A = a.A + (size_t)t * a.strideA;
+  const int pr = g * a.RP + tid;
+  const bool valid = (tid < a.RP) && (pr < m);
+  double* rowg = A + (size_t)(r0 + (valid ? pr : 0)) * ldk + c0;
+
+  // the row lives in registers, ROTATED: after tc columns P[q] holds column (q + tc) mod NB, so that the column
+  // being eliminated is always P[0] (static register indices inside a rolled loop: the fully unrolled variant
+  // is 49k instructions and instruction-cache bound)
+  double P[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) {
+    double2 v2 = make_double2(0.0, 0.0);
+    if (valid) v2 = *reinterpret_cast<const double2*>(rowg + c);
+    P[c] = v2.x; P[c + 1] = v2.y;
+  }
+  for (int e = tid; e < NB * QR_S; e += RG_THREADS) Gs[e] = 0.0;
+  if (tid < NB) taus[tid] = 0.0;
+
+  int par = 0;
+  auto exchange = [&]() {
+    __syncthreads();
+    if (CS == 1) {
+      if (tid < RG_XW) tot[tid] = mine[tid];
+    } else {
+      for (int e = tid; e < CS * RG_XW; e += RG_THREADS) {
+        const int dst = e / RG_XW, q = e % RG_XW;
+        double* remote = cluster.map_shared_rank(xch + (par * QR_MAXCS + g) * RG_XW, dst);
+        remote[q] = mine[q];
+      }
+      cluster.sync();
+      if (tid < RG_XW) {
+        double s = 0.0;
+        for (int q = 0; q < CS; ++q) s += xch[(par * QR_MAXCS + q) * RG_XW + tid];
+        tot[tid] = s;
+      }
+      par ^= 1;
+    }
+    __syncthreads();
+  };
+  __syncthreads();
+
+#pragma unroll 1
+  for (int tc = 0; tc < NB; ++tc) {
+    if (tc < nref) {
+      const double x = (valid && pr > tc) ? P[0] : 0.0;
+      // ---- transposing butterfly: lane q ends up with sum over the warp's rows of x * P[q]
       double t16[16], t8[8], t4[4], t2[2], t1;
       {
         const bool hi = lane & 16;
@@ -340,20 +390,20 @@ struct RgCol {
         t1 = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
       red[wid * NB + lane] = t1;
-      if (wid == 1) mine[NB + lane] = 0.0;        // row TC: zero unless this CTA owns it (owner overwrites below)
+      if (wid == 1) mine[NB + lane] = 0.0;        // row tc: zero unless this CTA owns it (owner overwrites below)
       __syncthreads();
       if (wid == 0) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < RG_NW; ++w) s += red[w * NB + lane];
-        mine[lane] = s;
+        mine[(lane + tc) & (NB - 1)] = s;         // back to natural column indices
       }
-      if (valid && pr == TC) {
+      if (valid && pr == tc) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) mine[NB + c] = P[c];
+        for (int q = 0; q < NB; ++q) mine[NB + ((q + tc) & (NB - 1))] = P[q];
       }
       exchange();
-      const double ssq = tot[TC], alpha = tot[NB + TC];
+      const double ssq = tot[tc], alpha = tot[NB + tc];
       double beta, tau, scale;
       if (ssq == 0.0) {
         beta = alpha; tau = 0.0; scale = 0.0;
@@ -362,79 +412,30 @@ struct RgCol {
         tau = (beta - alpha) / beta;
         scale = 1.0 / (alpha - beta);
       }
-      const double v = (!valid || pr < TC) ? 0.0 : ((pr == TC) ? 1.0 : x * scale);
+      const double v = (!valid || pr < tc) ? 0.0 : ((pr == tc) ? 1.0 : x * scale);
       const double tv = tau * v;
 #pragma unroll
-      for (int c = TC + 1; c < NB; ++c) P[c] = fma(-tv, fma(scale, tot[c], tot[NB + c]), P[c]);
-      if (valid && pr >= TC) P[TC] = (pr == TC) ? beta : v;
+      for (int q = 1; q < NB; ++q) {
+        if (q < NB - tc) {                        // columns c = tc + q > tc still to be eliminated
+          const int c = tc + q;
+          P[q] = fma(-tv, fma(scale, tot[c], tot[NB + c]), P[q]);
+        }
+      }
+      if (valid && pr >= tc) P[0] = (pr == tc) ? beta : v;
       if (wid == 0) {
-        if (lane < TC) Gs[lane * QR_S + TC] = fma(scale, tot[lane], tot[NB + lane]);
-        if (lane == 0) taus[TC] = tau;
+        if (lane < tc) Gs[lane * QR_S + tc] = fma(scale, tot[lane], tot[NB + lane]);
+        if (lane == 0) taus[tc] = tau;
       }
       __syncthreads();   // tot[] consumed before the next exchange overwrites it
-      RgCol<TC + 1>::run(P, pr, valid, nref, lane, wid, red, mine, tot, Gs, taus, exchange);
     }
-  }
-};
-template <>
-struct RgCol<NB> {
-  template <typename Ex>
-  static __device__ __forceinline__ void run(double (&)[NB], int, bool, int, int, int, double*, double*, const double*,
-                                             double*, double*, Ex&) {}
-};
-
-__global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
-  __shared__ __align__(16) double xch[2 * QR_MAXCS * RG_XW];
-  __shared__ double red[RG_NW * NB];
-  __shared__ double mine[RG_XW];
-  __shared__ double tot[RG_XW];
-  __shared__ double taus[NB];
-  __shared__ double Gs[NB * QR_S];
-  __shared__ double Ts[NB * QR_S];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int g = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
-  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = a.n, r0 = a.r0, c0 = a.c0, ldk = a.ldk;
-  const int m = n - r0;
-  const int nref = min(NB, m - 1);
-  double* A = a.A + (size_t)t * a.strideA;
-  const int pr = g * a.RP + tid;
-  const bool valid = (tid < a.RP) && (pr < m);
-  double* rowg = A + (size_t)(r0 + (valid ? pr : 0)) * ldk + c0;
-
-  double P[NB];
+    // rotate: the finished column moves to the end
+    {
+      const double p0 = P[0];
 #pragma unroll
-  for (int c = 0; c < NB; c += 2) {
-    double2 v2 = make_double2(0.0, 0.0);
-    if (valid) v2 = *reinterpret_cast<const double2*>(rowg + c);
-    P[c] = v2.x; P[c + 1] = v2.y;
-  }
-  for (int e = tid; e < NB * QR_S; e += RG_THREADS) { Gs[e] = 0.0; Ts[e] = 0.0; }
-  if (tid < NB) taus[tid] = 0.0;
-
-  int par = 0;
-  auto exchange = [&]() {
-    __syncthreads();
-    if (CS == 1) {
-      if (tid < RG_XW) tot[tid] = mine[tid];
-    } else {
-      for (int e = tid; e < CS * RG_XW; e += RG_THREADS) {
-        const int dst = e / RG_XW, q = e % RG_XW;
-        double* remote = cluster.map_shared_rank(xch + (par * QR_MAXCS + g) * RG_XW, dst);
-        remote[q] = mine[q];
-      }
-      cluster.sync();
-      if (tid < RG_XW) {
-        double s = 0.0;
-        for (int q = 0; q < CS; ++q) s += xch[(par * QR_MAXCS + q) * RG_XW + tid];
-        tot[tid] = s;
-      }
-      par ^= 1;
+      for (int q = 0; q < NB - 1; ++q) P[q] = P[q + 1];
+      P[NB - 1] = p0;
     }
-    __syncthreads();
-  };
-  __syncthreads();
-  RgCol<0>::run(P, pr, valid, nref, lane, wid, red, mine, tot, Gs, taus, exchange);
+  }
 
   // ---- compact-WY factor (dlarft, forward columnwise): lane a owns row a of T
   if (wid == 0 && g == 0) {
@@ -476,6 +477,7 @@ constexpr int SY_TILE = (SY_BM * SY_SD > SY_KC * SY_ST) ? SY_BM * SY_SD : SY_KC 
 constexpr int SY_STAGE = SY_TILE + SY_KC * SY_SV;
 constexpr int SY_NST = 2;
 constexpr int SY_ZW = 128;          // padded width of the Z-block partials
+constexpr int SY_MAXSPLIT = 4;      // split-K factor of the symm (partial Y buffers)
 
 struct SymmArgs {
   const double* A; size_t strideA; int ldk;
@@ -483,14 +485,41 @@ struct SymmArgs {
   double* Y;         // T x n x NB
   const double* Bq;  // T x n x ldb or null
   int ldb, nz;
-  double* Mpart;     // T x nblk x NB x NB
-  double* Zpart;     // T x nblk x NB x SY_ZW
-  int n, r0, nblk;
+  double* Mpart;     // T x nblk x NB x NB    (nblk = row blocks x splits)
+  double* Zpart;     // T x nzblk x NB x SY_ZW (nzblk = row blocks)
+  int n, r0, nblk, nzblk;
 };
+
+// one staged k-chunk (SY_KC columns) of the row block: direct tile [i][k], transposed tile [k][i], optionally
+// masked against the diagonal (only the chunks that cross it)
+template <bool TR, bool MK>
+__device__ __forceinline__ void symm_chunk(double (&acc)[2][4][2], const double* __restrict__ tile,
+                                           const double* __restrict__ vs, int wid, int fr, int fk, int i0, int j0) {
+  const double* ap = TR ? tile + fk * SY_ST + 16 * wid + fr : tile + (16 * wid + fr) * SY_SD + fk;
+  const double* vp = vs + fk * SY_SV + fr;
+#pragma unroll
+  for (int kk = 0; kk < SY_KC; kk += 4) {
+    double af[2], bf[4];
+#pragma unroll
+    for (int y = 0; y < 4; ++y) bf[y] = vp[kk * SY_SV + y * 8];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      af[x] = TR ? ap[kk * SY_ST + 8 * x] : ap[8 * x * SY_SD + kk];
+      if (MK) {
+        const int i = i0 + 16 * wid + 8 * x + fr, j = j0 + kk + fk;
+        if (TR ? (j <= i) : (j > i)) af[x] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+  }
+}
 
 __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int t = blockIdx.y, bx = blockIdx.x;
+  const int t = blockIdx.y, bx = blockIdx.x, sp = blockIdx.z, S = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int n = a.n, r0 = a.r0, ldk = a.ldk;
@@ -502,6 +531,8 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
   const int qd0 = (i0 - r0) / SY_KC;
   const int nd = min(SY_BM / SY_KC, nq - qd0);
   const int niter = nq + nd;
+  // split-K: this CTA handles iterations [it_lo, it_hi) of the row block; the S partial Y's are summed by wform
+  const int it_lo = (int)((long long)niter * sp / S), it_hi = (int)((long long)niter * (sp + 1) / S);
 
   // iteration -> (chunk, transposed, masked)
   auto decode = [&](int it, int& q, bool& tr, bool& mk) {
@@ -510,36 +541,38 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
     else if (it < qd0 + 2 * nd) { q = it - nd; tr = true; mk = true; }
     else { q = it - nd; tr = true; mk = false; }
   };
+  // per-thread copy geometry (fixed over the loop)
+  const int drow = tid >> 4, dpart = tid & 15;    // direct tile: rows drow + 16 s, 16-byte chunk dpart
+  const int trow = tid >> 6, tpart = tid & 63;    // transposed tile: rows trow + 4 s, chunk tpart
+  const double* dsrc = A + (size_t)(i0 + drow) * ldk + 2 * dpart;
+  const double* tsrc = A + (size_t)trow * ldk + i0 + 2 * tpart;
+  const bool tcol_ok = i0 + 2 * tpart < n;
   auto issue = [&](int it) {
     int q; bool tr, mk;
     decode(it, q, tr, mk);
     (void)mk;
-    double* tile = smem + (size_t)(it % SY_NST) * SY_STAGE;
+    double* tile = smem + (size_t)((it - it_lo) % SY_NST) * SY_STAGE;
     double* vs = tile + SY_TILE;
     const int j0 = r0 + SY_KC * q;
     if (!tr) {
+      const bool cok = j0 + 2 * dpart < n;
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int c = tid + 256 * s, row = c >> 4, part = c & 15;
-        const bool ok = (i0 + row < n) && (j0 + 2 * part < n);
-        const double* src = ok ? A + (size_t)(i0 + row) * ldk + j0 + 2 * part : A;
-        cp_async16(tile + row * SY_SD + 2 * part, src, ok);
+        const bool ok = cok && (i0 + drow + 16 * s < n);
+        cp_async16(tile + (drow + 16 * s) * SY_SD + 2 * dpart, ok ? dsrc + (size_t)16 * s * ldk + j0 : A, ok);
       }
     } else {
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int c = tid + 256 * s, row = c >> 6, part = c & 63;
-        const bool ok = (j0 + row < n) && (i0 + 2 * part < n);
-        const double* src = ok ? A + (size_t)(j0 + row) * ldk + i0 + 2 * part : A;
-        cp_async16(tile + row * SY_ST + 2 * part, src, ok);
+        const bool ok = tcol_ok && (j0 + trow + 4 * s < n);
+        cp_async16(tile + (trow + 4 * s) * SY_ST + 2 * tpart, ok ? tsrc + (size_t)(j0 + 4 * s) * ldk : A, ok);
       }
     }
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int c = tid + 256 * s, row = c >> 4, part = c & 15;
+      const int row = drow + 16 * s;
       const bool ok = (j0 + row < n);
-      const double* src = ok ? V + (size_t)(j0 + row) * NB + 2 * part : V;
-      cp_async16(vs + row * SY_SV + 2 * part, src, ok);
+      cp_async16(vs + row * SY_SV + 2 * dpart, ok ? V + (size_t)(j0 + row) * NB + 2 * dpart : V, ok);
     }
   };
 
@@ -549,36 +582,24 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
 #pragma unroll
     for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
 
-  issue(0);
+  if (it_lo < it_hi) issue(it_lo);
   cp_async_commit();
-  for (int it = 0; it < niter; ++it) {
-    if (it + 1 < niter) issue(it + 1);
+  for (int it = it_lo; it < it_hi; ++it) {
+    if (it + 1 < it_hi) issue(it + 1);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
     int q; bool tr, mk;
     decode(it, q, tr, mk);
-    const double* tile = smem + (size_t)(it % SY_NST) * SY_STAGE;
+    const double* tile = smem + (size_t)((it - it_lo) % SY_NST) * SY_STAGE;
     const double* vs = tile + SY_TILE;
     const int j0 = r0 + SY_KC * q;
-#pragma unroll
-    for (int kk = 0; kk < SY_KC; kk += 4) {
-      double af[2], bf[4];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) bf[y] = vs[(kk + fk) * SY_SV + y * 8 + fr];
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        const int rl = 16 * wid + 8 * x + fr;
-        af[x] = tr ? tile[(kk + fk) * SY_ST + rl] : tile[rl * SY_SD + kk + fk];
-        if (mk) {
-          const int i = i0 + rl, j = j0 + kk + fk;
-          if (tr ? (j <= i) : (j > i)) af[x] = 0.0;
-        }
-      }
-#pragma unroll
-      for (int x = 0; x < 2; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+    if (!mk) {
+      if (!tr) symm_chunk<false, false>(acc, tile, vs, wid, fr, fk, i0, j0);
+      else symm_chunk<true, false>(acc, tile, vs, wid, fr, fk, i0, j0);
+    } else {
+      if (!tr) symm_chunk<false, true>(acc, tile, vs, wid, fr, fk, i0, j0);
+      else symm_chunk<true, true>(acc, tile, vs, wid, fr, fk, i0, j0);
     }
     __syncthreads();
   }
@@ -587,7 +608,7 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
   // ---- epilogue: Y rows, then the partial products V_I^T Y_I and V_I^T B_I of this row block
   double* Ys = smem;                       // SY_BM x (NB + 1)
   double* Vs = Ys + SY_BM * (NB + 1);      // SY_BM x (NB + 1)
-  double* Y = a.Y + (size_t)t * n * NB;
+  double* Y = a.Y + ((size_t)sp * gridDim.y + t) * n * NB;
 #pragma unroll
   for (int x = 0; x < 2; ++x) {
     const int rl = 16 * wid + 8 * x + fr, i = i0 + rl;
@@ -611,11 +632,11 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) mp[u] = fma(Vs[rl * (NB + 1) + wid + 8 * u], yv, mp[u]);
     }
-    double* Mp = a.Mpart + ((size_t)t * a.nblk + bx) * NB * NB;
+    double* Mp = a.Mpart + ((size_t)t * a.nblk + bx * S + sp) * NB * NB;
 #pragma unroll
     for (int u = 0; u < 4; ++u) Mp[(wid + 8 * u) * NB + lane] = mp[u];
   }
-  if (a.Bq && a.nz > 0) {
+  if (a.Bq && a.nz > 0 && sp == 0) {
     const double* Bq = a.Bq + (size_t)t * n * a.ldb;
     const int z = tid & 127, c1g = tid >> 7;   // 2 groups of 16 reflector columns
     double zp[16];
@@ -628,7 +649,7 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
         for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[rl * (NB + 1) + 16 * c1g + u], bv, zp[u]);
       }
     }
-    double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW;
+    double* Zp = a.Zpart + ((size_t)t * a.nzblk + bx) * NB * SY_ZW;
 #pragma unroll
     for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
   }
@@ -639,7 +660,7 @@ struct ReduceArgs {
   const double* Mpart; const double* Zpart;
   double* Mred;   // T x NB x NB
   double* Zred;   // T x NB x SY_ZW
-  int nblk, has_z;
+  int nblk, nzblk, has_z;
 };
 
 __global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
@@ -653,16 +674,17 @@ __global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
     a.Mred[(size_t)t * NM + e] = s;
   } else if (e < NM + NZ && a.has_z) {
     const int ez = e - NM;
-    const double* p = a.Zpart + (size_t)t * a.nblk * NZ + ez;
+    const double* p = a.Zpart + (size_t)t * a.nzblk * NZ + ez;
     double s = 0.0;
-    for (int b = 0; b < a.nblk; ++b) s += p[(size_t)b * NZ];
+    for (int b = 0; b < a.nzblk; ++b) s += p[(size_t)b * NZ];
     a.Zred[(size_t)t * NZ + ez] = s;
   }
 }
 
 // ------------------------------------------------------------------ W and the Z-block update
 struct WformArgs {
-  const double* V; const double* Y; double* W;   // T x n x NB
+  const double* V; const double* Y; double* W;   // T x n x NB  (Y: nsplit partial buffers of T x n x NB)
+  int nsplit, T;
   const double* Tf; size_t tf_stride;            // this panel's slot
   const double* Mred; const double* Zred;
   double* Bq; int ldb, nz;
@@ -699,7 +721,10 @@ __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
     const int rl = e / NB, c = e % NB;
     const bool ok = i0 + rl < n;
     Vs[rl * (NB + 1) + c] = ok ? V[(size_t)(i0 + rl) * NB + c] : 0.0;
-    Xs[rl * (NB + 1) + c] = ok ? Y[(size_t)(i0 + rl) * NB + c] : 0.0;
+    double yv = 0.0;
+    if (ok)
+      for (int sp = 0; sp < a.nsplit; ++sp) yv += Y[(size_t)sp * a.T * n * NB + (size_t)(i0 + rl) * NB + c];
+    Xs[rl * (NB + 1) + c] = yv;
   }
   __syncthreads();
   // T^T M and T^T (V^T B) in registers, then in place:  out[a][c] = sum_{k <= a} T[k][a] in[k][c]
@@ -819,53 +844,158 @@ __global__ void __launch_bounds__(256, 2) syr2k_kernel(Syr2kArgs a) {
     cp_async16(Bs + row * S2_S + 2 * part, src, ok);
   }
   cp_async_commit();
+  const int wm = wid >> 1, wn = wid & 1;   // 4 x 2 warps, warp tile 32 x 32
+  // accumulators start at -A (loaded while the operand copies are in flight); the result is stored as -acc
   double acc[4][4][2];
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
+  for (int x = 0; x < 4; ++x) {
+    const int i = i0 + 32 * wm + 8 * x + fr;
 #pragma unroll
-    for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-  const int wm = wid >> 1, wn = wid & 1;   // 4 x 2 warps, warp tile 32 x 32
+    for (int y = 0; y < 4; ++y) {
+      const int j = j0 + 32 * wn + 8 * y + 2 * fk;
+      const double* p = A + (size_t)i * ldk + j;
+      double2 o = make_double2(0.0, 0.0);
+      if (i < n) {
+        if (j + 1 <= i) o = ldcg2(reinterpret_cast<const double2*>(p));
+        else if (j <= i) o.x = ldcg(p);
+      }
+      acc[x][y][0] = -o.x;
+      acc[x][y][1] = -o.y;
+    }
+  }
   cp_async_wait<0>();
   __syncthreads();
+  {
+    const double* ap = As + (32 * wm + fr) * S2_S + fk;
+    const double* bp = Bs + (32 * wn + fr) * S2_S + fk;
 #pragma unroll 4
-  for (int kk = 0; kk < S2_K; kk += 4) {
-    double af[4], bf[4];
+    for (int kk = 0; kk < S2_K; kk += 4) {
+      double af[4], bf[4];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      af[x] = As[(32 * wm + 8 * x + fr) * S2_S + kk + fk];
-      bf[x] = Bs[(32 * wn + 8 * x + fr) * S2_S + kk + fk];
+      for (int x = 0; x < 4; ++x) {
+        af[x] = ap[8 * x * S2_S + kk];
+        bf[x] = bp[8 * x * S2_S + kk];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
     }
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
   }
 #pragma unroll
   for (int x = 0; x < 4; ++x) {
     const int i = i0 + 32 * wm + 8 * x + fr;
     if (i < n) {
-      double2 o[4];
-      bool full[4];
-#pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        const int j = j0 + 32 * wn + 8 * y + 2 * fk;
-        full[y] = (j + 1 <= i);
-        const double* p = A + (size_t)i * ldk + j;
-        if (full[y]) {
-          o[y] = ldcg2(reinterpret_cast<const double2*>(p));
-        } else {
-          o[y].x = (j <= i) ? ldcg(p) : 0.0;
-          o[y].y = 0.0;
-        }
-      }
 #pragma unroll
       for (int y = 0; y < 4; ++y) {
         const int j = j0 + 32 * wn + 8 * y + 2 * fk;
         double* p = A + (size_t)i * ldk + j;
-        if (full[y]) {
-          *reinterpret_cast<double2*>(p) = make_double2(o[y].x - acc[x][y][0], o[y].y - acc[x][y][1]);
-        } else if (j <= i) {
-          p[0] = o[y].x - acc[x][y][0];
+        if (j + 1 <= i) *reinterpret_cast<double2*>(p) = make_double2(-acc[x][y][0], -acc[x][y][1]);
+        else if (j <= i) p[0] = -acc[x][y][0];
+      }
+    }
+  }
+}
+
+// ---- row-persistent variant: one CTA keeps [V_I | W_I] of its 128-row block in shared memory and walks a chunk of
+// 32-column tiles of that block row; the next tile's [W_J | V_J] (cp.async, double buffered) and its A values
+// (registers) are fetched while the current tile is on the tensor cores.
+constexpr int S3_BM = 128, S3_BN = 32, S3_CH = 16;   // tile rows / cols, tiles per CTA
+
+__global__ void __launch_bounds__(256, 2) syr2k_row_kernel(Syr2kArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int t = blockIdx.z;
+  const int n = a.n, r0 = a.r0, ldk = a.ldk;
+  const int i0 = r0 + S3_BM * blockIdx.y;
+  // 32-column tiles of this block row that touch the lower triangle: j0 = r0 + 32 jt <= i0 + 127, j0 < n
+  const int njt = min((i0 + S3_BM - r0) / S3_BN, (n - r0 + S3_BN - 1) / S3_BN);
+  const int jt_lo = S3_CH * blockIdx.x, jt_hi = min(njt, jt_lo + S3_CH);
+  if (jt_lo >= jt_hi) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  double* A = a.A + (size_t)t * a.strideA;
+  const double* V = a.V + (size_t)t * n * NB;
+  const double* W = a.W + (size_t)t * n * NB;
+  double* As = smem;                      // S3_BM x S2_S : [V_I | W_I]
+  double* Bs = As + S3_BM * S2_S;         // 2 x S3_BN x S2_S : [W_J | V_J]
+  const int wm = wid >> 1, wn = wid & 1;  // 4 x 2 warps, warp tile 32 x 16
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    const int c = tid + 256 * s, row = c >> 5, part = c & 31;
+    const bool ok = i0 + row < n;
+    const double* base = (part < 16) ? V : W;
+    cp_async16(As + row * S2_S + 2 * part, ok ? base + (size_t)(i0 + row) * NB + 2 * (part & 15) : base, ok);
+  }
+  auto issue_b = [&](int jt) {
+    double* dst = Bs + (size_t)((jt - jt_lo) & 1) * S3_BN * S2_S;
+    const int j0 = r0 + S3_BN * jt;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int c = tid + 256 * s, row = c >> 5, part = c & 31;
+      const bool ok = j0 + row < n;
+      const double* base = (part < 16) ? W : V;
+      cp_async16(dst + row * S2_S + 2 * part, ok ? base + (size_t)(j0 + row) * NB + 2 * (part & 15) : base, ok);
+    }
+  };
+  double nxt[4][2][2];
+  auto load_a = [&](int jt) {
+    const int j0 = r0 + S3_BN * jt;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int i = i0 + 32 * wm + 8 * x + fr;
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const int j = j0 + 16 * wn + 8 * y + 2 * fk;
+        const double* p = A + (size_t)i * ldk + j;
+        double2 o = make_double2(0.0, 0.0);
+        if (i < n) {
+          if (j + 1 <= i) o = ldcg2(reinterpret_cast<const double2*>(p));
+          else if (j <= i) o.x = ldcg(p);
+        }
+        nxt[x][y][0] = o.x;
+        nxt[x][y][1] = o.y;
+      }
+    }
+  };
+  issue_b(jt_lo);
+  cp_async_commit();
+  load_a(jt_lo);
+  const double* ap = As + (32 * wm + fr) * S2_S + fk;
+  for (int jt = jt_lo; jt < jt_hi; ++jt) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (jt + 1 < jt_hi) issue_b(jt + 1);
+    cp_async_commit();
+    double acc[4][2][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) { acc[x][y][0] = -nxt[x][y][0]; acc[x][y][1] = -nxt[x][y][1]; }
+    if (jt + 1 < jt_hi) load_a(jt + 1);
+    const double* bp = Bs + (size_t)((jt - jt_lo) & 1) * S3_BN * S2_S + (16 * wn + fr) * S2_S + fk;
+#pragma unroll 4
+    for (int kk = 0; kk < S2_K; kk += 4) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) af[x] = ap[8 * x * S2_S + kk];
+#pragma unroll
+      for (int y = 0; y < 2; ++y) bf[y] = bp[8 * y * S2_S + kk];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+    }
+    const int j0 = r0 + S3_BN * jt;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int i = i0 + 32 * wm + 8 * x + fr;
+      if (i < n) {
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          const int j = j0 + 16 * wn + 8 * y + 2 * fk;
+          double* p = A + (size_t)i * ldk + j;
+          if (j + 1 <= i) *reinterpret_cast<double2*>(p) = make_double2(-acc[x][y][0], -acc[x][y][1]);
+          else if (j <= i) p[0] = -acc[x][y][0];
         }
       }
     }
@@ -1023,9 +1153,9 @@ size_t band_workspace(const Plan* pl, int T) {
   const size_t n = pl->n;
   const size_t nblk = (n + SY_BM - 1) / SY_BM;
   size_t b = 0;
-  b += 3 * align_up(T * n * NB * sizeof(double), 256);                       // V, Y, W
+  b += (2 + SY_MAXSPLIT) * align_up(T * n * NB * sizeof(double), 256);       // V, W, Y (split-K partials)
   b += align_up((size_t)T * (band_npanels(pl->n) + 1) * NB * NB * sizeof(double), 256);   // T factors
-  b += align_up((size_t)T * nblk * NB * NB * sizeof(double), 256);           // Mpart
+  b += align_up((size_t)T * nblk * SY_MAXSPLIT * NB * NB * sizeof(double), 256);   // Mpart
   b += align_up((size_t)T * nblk * NB * SY_ZW * sizeof(double), 256);        // Zpart
   b += align_up((size_t)T * NB * NB * sizeof(double), 256);                  // Mred
   b += align_up((size_t)T * NB * SY_ZW * sizeof(double), 256);               // Zred
@@ -1040,11 +1170,11 @@ bool band_carve(const Plan* pl, int T, Carver& cv, BandBuffers& bb) {
   const size_t n = pl->n;
   const size_t nblk = (n + SY_BM - 1) / SY_BM;
   bb.V = cv.take<double>(T * n * NB);
-  bb.Y = cv.take<double>(T * n * NB);
+  bb.Y = cv.take<double>((size_t)SY_MAXSPLIT * T * n * NB);
   bb.W = cv.take<double>(T * n * NB);
   bb.tf_stride = (size_t)(band_npanels(pl->n) + 1) * NB * NB;
   bb.Tf = cv.take<double>((size_t)T * bb.tf_stride);
-  bb.Mpart = cv.take<double>((size_t)T * nblk * NB * NB);
+  bb.Mpart = cv.take<double>((size_t)T * nblk * SY_MAXSPLIT * NB * NB);
   bb.Zpart = cv.take<double>((size_t)T * nblk * NB * SY_ZW);
   bb.Mred = cv.take<double>((size_t)T * NB * NB);
   bb.Zred = cv.take<double>((size_t)T * NB * SY_ZW);
@@ -1081,16 +1211,26 @@ static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B,
   const int n = pl->n, m = n - r0;
   const size_t strideA = (size_t)n * ldk;
   const int nblk = (m + SY_BM - 1) / SY_BM;
+  int rc;
+  // split-K so that the launch fills the machine (2 CTAs per SM) at least ~twice, while every CTA keeps a few chunks
+  int S = 1;
+  {
+    const int slots = 2 * pl->sm_count;
+    const int niter_min = (m + SY_KC - 1) / SY_KC;
+    while (S < SY_MAXSPLIT && nblk * T * S < 2 * slots && niter_min / (2 * S) >= 4) S *= 2;
+  }
   {
     SymmArgs a;
     a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Y = bb.Y; a.Bq = B; a.ldb = ldb; a.nz = nz;
-    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk;
-    symm_kernel<<<dim3(nblk, T), 256, SY_NST * SY_STAGE * sizeof(double), st>>>(a);
+    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk * S; a.nzblk = nblk;
+    if ((rc = profile_mark_begin(PROF_SYMM, st))) return rc;
+    symm_kernel<<<dim3(nblk, T, S), 256, SY_NST * SY_STAGE * sizeof(double), st>>>(a);
     CHD_LAUNCHED();
+    if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
   }
   {
     ReduceArgs a;
-    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.Mred = bb.Mred; a.Zred = bb.Zred; a.nblk = nblk;
+    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.Mred = bb.Mred; a.Zred = bb.Zred; a.nblk = nblk * S; a.nzblk = nblk;
     a.has_z = (B && nz > 0) ? 1 : 0;
     const int total = NB * NB + (a.has_z ? NB * SY_ZW : 0);
     reduce_kernel<<<dim3((total + 255) / 256, T), 256, 0, st>>>(a);
@@ -1098,17 +1238,29 @@ static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B,
   }
   {
     WformArgs a;
-    a.V = bb.V; a.Y = bb.Y; a.W = bb.W; a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride;
+    a.V = bb.V; a.Y = bb.Y; a.W = bb.W; a.nsplit = S; a.T = T;
+    a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride;
     a.Mred = bb.Mred; a.Zred = bb.Zred; a.Bq = B; a.ldb = ldb; a.nz = nz; a.n = n; a.r0 = r0;
+    if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
     wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
     CHD_LAUNCHED();
+    if ((rc = profile_mark_end(PROF_WFORM, st))) return rc;
   }
   {
     Syr2kArgs a;
     a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.W = bb.W; a.n = n; a.r0 = r0;
-    const dim3 grid((m + S2_BN - 1) / S2_BN, (m + S2_BM - 1) / S2_BM, T);
-    syr2k_kernel<<<grid, 256, (S2_BM + S2_BN) * S2_S * sizeof(double), st>>>(a);
+    static const int variant = getenv("CHD_SYR2K") ? atoi(getenv("CHD_SYR2K")) : 1;   // 0: one tile per CTA
+    if ((rc = profile_mark_begin(PROF_SYR2K, st))) return rc;
+    if (variant == 0) {
+      const dim3 grid((m + S2_BN - 1) / S2_BN, (m + S2_BM - 1) / S2_BM, T);
+      syr2k_kernel<<<grid, 256, (S2_BM + S2_BN) * S2_S * sizeof(double), st>>>(a);
+    } else {
+      const int ntile = (m + S3_BN - 1) / S3_BN;
+      const dim3 grid((ntile + S3_CH - 1) / S3_CH, (m + S3_BM - 1) / S3_BM, T);
+      syr2k_row_kernel<<<grid, 256, (S3_BM + 2 * S3_BN) * S2_S * sizeof(double), st>>>(a);
+    }
     CHD_LAUNCHED();
+    if ((rc = profile_mark_end(PROF_SYR2K, st))) return rc;
   }
   return CHD_OK;
 }
@@ -1124,6 +1276,8 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
     CHD_CUDA(cudaFuncSetAttribute(syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((S2_BM + S2_BN) * S2_S * sizeof(double))));
     CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+    CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((S3_BM + 2 * S3_BN) * S2_S * sizeof(double))));
     CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
     CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1178,6 +1332,7 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
     at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cfg.stream = st;
+    if ((rc = profile_mark_begin(PROF_QR, st))) return rc;
     int rcs = 1;
     while (rcs < reg_max_cs && (m + rcs - 1) / rcs > RG_THREADS) rcs *= 2;
     if (reg_max_cs > 0 && (m + rcs - 1) / rcs <= RG_THREADS) {
@@ -1196,6 +1351,7 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
       CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_kernel, a));
     }
     g_launches.fetch_add(1);
+    if ((rc = profile_mark_end(PROF_QR, st))) return rc;
     if ((rc = trailing_launch(pl, K, ldk, T, B, ldb, nz, r0, p, bb, st))) return rc;
   }
   band_extract_kernel<<<dim3(min((n * CHD_CHASE_LD + 255) / 256, 1024), T), 256, 0, st>>>(K, strideA, ldk, n,
@@ -1212,8 +1368,11 @@ int backtransform2_launch(const Plan* pl, const double* K, int ldk, const BandBu
   a.npanel = band_npanels(pl->n);
   a.RPB = (pl->n + BT_CS - 1) / BT_CS;
   const size_t smem = (2 * BT_CS * NB + (BT_THREADS / 32) * (NB + 1) + 2 * NB + NB * (NB + 1) + a.RPB) * sizeof(double);
+  int rc;
+  if ((rc = profile_mark_begin(PROF_BACK, st))) return rc;
   backtransform2_kernel<<<dim3(BT_CS, T), BT_THREADS, smem, st>>>(a);
   CHD_LAUNCHED();
+  if ((rc = profile_mark_end(PROF_BACK, st))) return rc;
   return CHD_OK;
 }
 

@@ -190,8 +190,11 @@ int band_solve_launch(const Plan* pl, const double* bandS, double* Lg, const dou
   BandSolveArgs a;
   a.bandS = bandS; a.Lg = Lg; a.gu = gu; a.gamma = nullptr; a.Bq = Bq; a.ldb = ldb; a.nz = Bq ? nz : 0; a.x = x;
   a.noise = noise; a.z_low = z_low; a.z_high = z_high; a.out_stride = out_stride; a.n = pl->n;
+  int rc;
+  if ((rc = profile_mark_begin(PROF_SOLVE, st))) return rc;
   band_solve_kernel<<<T, BS_THREADS, 0, st>>>(a);
   CHD_LAUNCHED();
+  if ((rc = profile_mark_end(PROF_SOLVE, st))) return rc;
   return CHD_OK;
 }
 

@@ -206,8 +206,11 @@ int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e,
       ChaseArgs a;
       a.bandW = bandW + (size_t)t0 * n * CLD; a.prog = prog + (size_t)t0 * n; a.n = n;
       void* params[] = {&a};
+      int prc;
+      if ((prc = profile_mark_begin(PROF_CHASE, st))) return prc;
       CHD_CUDA(cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(per, cnt), dim3(CH_WARPS * 32), params, smem, st));
       g_launches.fetch_add(1);
+      if ((prc = profile_mark_end(PROF_CHASE, st))) return prc;
       t0 += cnt;
     }
   }

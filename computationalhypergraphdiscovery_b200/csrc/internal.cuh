@@ -53,8 +53,14 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
                size_t act_stride, int prune, int32_t* pruned, size_t pruned_stride, void* ws, size_t ws_bytes,
                cudaStream_t st, const double* P, int ldk);
 int removed_vars_launch(const uint8_t* w_prev, const uint8_t* w_new, int count, uint8_t* wrem, cudaStream_t st);
+enum ProfCat { PROF_TRIDIAG = 0, PROF_SYMM = 1, PROF_SYR2K = 2, PROF_QR = 3, PROF_CHASE = 4, PROF_WFORM = 5,
+               PROF_SOLVE = 6, PROF_BACK = 7 };
 int profile_enable(int on);
+bool profile_on();
+int profile_mark_begin(int cat, cudaStream_t st);
+int profile_mark_end(int cat, cudaStream_t st);
 int profile_read(double* total_ms, int* launches);
+int profile_read_cat(int cat, double* total_ms, int* launches);
 int active_vars_launch(const uint8_t* w0, const uint8_t* alive, const int32_t* cluster_of, int N, int C, int T,
                        uint8_t* w, cudaStream_t st);
 

@@ -869,7 +869,8 @@ __global__ void __launch_bounds__(512) backtransform_kernel(BackArgs a) {
 
 // ------------------------------------------------------------------ host side
 static bool g_prof_on = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct ProfSpan { cudaEvent_t e0, e1; int cat; };
+static std::vector<ProfSpan> g_prof_events;
 static size_t g_prof_used = 0;
 
 int profile_enable(int on) {
@@ -878,18 +879,48 @@ int profile_enable(int on) {
   return CHD_OK;
 }
 
-int profile_read(double* total_ms, int* launches) {
-  double tot = 0.0;
-  for (size_t i = 0; i < g_prof_used; ++i) {
-    CHD_CUDA(cudaEventSynchronize(g_prof_events[i].second));
-    float ms = 0.f;
-    CHD_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
-    tot += ms;
+bool profile_on() { return g_prof_on; }
+
+// Brackets one launch (category `cat`) by CUDA events on its own stream.
+int profile_mark_begin(int cat, cudaStream_t st) {
+  if (!g_prof_on) return CHD_OK;
+  if (g_prof_used == g_prof_events.size()) {
+    ProfSpan sp;
+    CHD_CUDA(cudaEventCreate(&sp.e0));
+    CHD_CUDA(cudaEventCreate(&sp.e1));
+    sp.cat = cat;
+    g_prof_events.push_back(sp);
   }
-  if (total_ms) *total_ms = tot;
-  if (launches) *launches = (int)g_prof_used;
+  g_prof_events[g_prof_used].cat = cat;
+  CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].e0, st));
   return CHD_OK;
 }
+
+int profile_mark_end(int cat, cudaStream_t st) {
+  (void)cat;
+  if (!g_prof_on) return CHD_OK;
+  CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].e1, st));
+  ++g_prof_used;
+  return CHD_OK;
+}
+
+int profile_read_cat(int cat, double* total_ms, int* launches) {
+  double tot = 0.0;
+  int cnt = 0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (cat >= 0 && g_prof_events[i].cat != cat) continue;
+    CHD_CUDA(cudaEventSynchronize(g_prof_events[i].e1));
+    float ms = 0.f;
+    CHD_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].e0, g_prof_events[i].e1));
+    tot += ms;
+    ++cnt;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = cnt;
+  return CHD_OK;
+}
+
+int profile_read(double* total_ms, int* launches) { return profile_read_cat(PROF_TRIDIAG, total_ms, launches); }
 
 size_t tridiag_smem_bytes(const Plan* pl) {
   const int chunks = (pl->n + TD_RB - 1) / TD_RB;
@@ -975,21 +1006,11 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
     b.pgram = tb.pgram + (size_t)t0 * n * pl->nb;
     b.bar = tb.bar + t0;
     void* params[] = {&b};
-    if (g_prof_on) {
-      if (g_prof_used == g_prof_events.size()) {
-        cudaEvent_t e0, e1;
-        CHD_CUDA(cudaEventCreate(&e0));
-        CHD_CUDA(cudaEventCreate(&e1));
-        g_prof_events.emplace_back(e0, e1);
-      }
-      CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].first, st));
-    }
+    int prc;
+    if ((prc = profile_mark_begin(PROF_TRIDIAG, st))) return prc;
     CHD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(pl->G, cnt), dim3(pl->threads), params, smem, st));
     g_launches.fetch_add(1);
-    if (g_prof_on) {
-      CHD_CUDA(cudaEventRecord(g_prof_events[g_prof_used].second, st));
-      ++g_prof_used;
-    }
+    if ((prc = profile_mark_end(PROF_TRIDIAG, st))) return prc;
   }
   if (dbg_on) {
     unsigned long long h[8];

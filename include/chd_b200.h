@@ -180,9 +180,16 @@ int chd_plan_set_two_stage(chd_plan* plan, int on);
  * (ms) and the number of launches since the last chd_profile_enable(1). */
 int chd_profile_enable(int on);
 int chd_profile_read(double* total_ms, int* launches);
+/* Per-kernel variant: category 0 = one-stage tridiagonalisation, 1 = symm (Y = A22 V), 2 = syr2k (trailing update),
+ * 3 = panel QR, 4 = bulge chasing, 5 = W formation, 6 = band solve + Z-test, 7 = back-transformation; -1 = all. */
+int chd_profile_read_cat(int category, double* total_ms, int* launches);
+/* 1 if the plan runs the two-stage reduction (default; env CHD_TWO_STAGE=0 or chd_plan_set_two_stage to change). */
+int chd_plan_two_stage(const chd_plan* plan);
 /* FP64 tensor-core (DMMA) throughput probe: runs `iters` back-to-back m8n8k4 chains per warp on
  * the whole GPU and returns the measured TFLOP/s (host-synchronising; used for the roofline peak). */
 int chd_dmma_peak(int iters, double* tflops);
+/* FP64 pipe probe: mode 0 = DMMA only, 1 = DFMA only, 2 = both interleaved at equal flops; returns TFLOP/s. */
+int chd_fp64_probe(int iters, int mode, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -93,7 +93,11 @@ def prune_step(spec, X, active_modes, ga, yb, key, gamma_min, has_clusters, exps
     active_modes = active_modes.copy()
     active_modes[j, :] = 0.0
     K = gram(spec, X, X, np.sum(active_modes, axis=0), exps)
-    yb, noise, zl, zh, gamma, key = perform_regression_and_find_gamma(K, ga, gamma_min, key)
+    info = {}
+    yb, noise, zl, zh, gamma, key = perform_regression_and_find_gamma(K, ga, gamma_min, key, info)
+    # the value REG:134 would have returned had the BFGS `success` flag come out the other way (test bookkeeping:
+    # near convergence that flag is decided by rounding noise of the loss)
+    prune_step.last_alt_gamma = info["median"] if info["success"] else info["x"]
     return active_modes, yb, gamma, key, act, noise, zl, zh
 
 
@@ -173,6 +177,7 @@ def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, 
     N = X.shape[1]
     anc = [np.sum(active_modess, axis=1)]
     noises, zl, zh, gam, ybl, acts = [noise], [zlo], [zhi], [gammas], [ybs], []
+    alts = [np.full(Tk, np.nan)]
     active = active_modess.copy()
     ybs = ybs.copy()
     keys = keys.copy()
@@ -195,10 +200,13 @@ def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, 
         nz = np.empty(Tk)
         l = np.empty(Tk)
         h = np.empty(Tk)
+        alt = np.empty(Tk)
         for t in range(Tk):
             (a_new[t], yb_new[t], g_new[t], k_new[t], act[t], nz[t], l[t], h[t]) = prune_step(
                 spec, X, active[t], gas[t], ybs[t], keys[t], gamma_min_kernel[t], has_clusters, exps)
+            alt[t] = prune_step.last_alt_gamma
         active, ybs, keys = a_new, yb_new, k_new
+        one_step.alt = alt
         return g_new, act, nz, l, h
 
     for step in range(loop_number):
@@ -208,6 +216,7 @@ def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, 
         g_new, act, nz, l, h = one_step()
         anc.append(np.sum(active, axis=1))
         noises.append(nz); zl.append(l); zh.append(h); acts.append(act); gam.append(g_new); ybl.append(ybs)
+        alts.append(one_step.alt)
         if np.all(active == 0):                                         # MAIN:659-660
             break
     if loop_number == 0:                                                # MAIN:662-691
@@ -217,7 +226,7 @@ def prune_ancestors(spec, X, active_modess, gas, ybs, gammas, keys, noise, zlo, 
     return dict(active=np.stack(anc, axis=1), noises=np.stack(noises, axis=1),
                 Z_lows=np.stack(zl, axis=1), Z_highs=np.stack(zh, axis=1),
                 activations=np.stack(acts, axis=1), gammas=np.stack(gam, axis=1),
-                ybs=np.stack(ybl, axis=1))
+                ybs=np.stack(ybl, axis=1), alt_gammas=np.stack(alts, axis=1))
 
 
 # ------------------------------------------------------------------------------ fit

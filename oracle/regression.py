@@ -63,7 +63,7 @@ def find_gamma(eigenvalues, Pga, gamma_min, info=None):
     guess = median if best == 0 else float(GRID[best])               # REG:132
     x, success, k = minimize_bfgs_1d(make_loss(eigenvalues, Pga), guess)  # REG:133
     if info is not None:
-        info.update(best=best, guess=guess, median=median, success=success, k=k)
+        info.update(best=best, guess=guess, median=median, success=success, k=k, x=float(x))
     return float(x) if success else median                            # REG:134
 
 
