@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
   const int tx = tid & 15, ty = tid >> 4;
   const uint8_t* wt = w + (size_t)t * N;
   const double* y = yb + (size_t)t * n;
+  __shared__ double etab[64];
+  exp_table_load(etab);
   for (int q = tid; q < C * 8; q += 256) sacc[q] = 0.0;
   __syncthreads();
   const int tb = (n + GA_TILE - 1) / GA_TILE;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const double df = xi[a] - xj[b];
-          P[a][b] *= 1.0 + exp(-(df * df) * inv2l2);
+          P[a][b] *= 1.0 + exp_nonpos(-(df * df) * inv2l2, etab);
         }
     }
 #pragma unroll
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const double df = xi[a] - xj[b];
-            F[a][b] *= 1.0 + exp(-(df * df) * inv2l2);
+            F[a][b] *= 1.0 + exp_nonpos(-(df * df) * inv2l2, etab);
           }
       }
       if (!any) continue;

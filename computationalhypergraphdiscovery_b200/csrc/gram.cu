@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
   //   2: P <- P / prod_{d removed}(1 + E_d) with the removed variables gathered in Xr (n x ldp), no full product.
   __shared__ __align__(16) double As[GT * GS];
   __shared__ __align__(16) double Bs[GT * GS];
+  __shared__ double etab[64];
+  exp_table_load(etab);     // visible after the first __syncthreads of the k-loop / the divisor loop
   const int t = blockIdx.y;
   int bi, bj;
   if (SYMM) {
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               double df = xr[a] - xc[b][c];
-              prod[a][b][c] *= 1.0 + exp(-(df * df) * inv2l2);
+              prod[a][b][c] *= 1.0 + exp_nonpos(-(df * df) * inv2l2, etab);
             }
       }
     }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               double df = xr[a] - xc[b][c];
-              prod[a][b][c] *= 1.0 + exp(-(df * df) * inv2l2);
+              prod[a][b][c] *= 1.0 + exp_nonpos(-(df * df) * inv2l2, etab);
             }
       }
       __syncthreads();
