@@ -727,24 +727,23 @@ __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
     Xs[rl * (NB + 1) + c] = yv;
   }
   __syncthreads();
-  // T^T M and T^T (V^T B) in registers, then in place:  out[a][c] = sum_{k <= a} T[k][a] in[k][c]
-  double tm[4], tz[16];
+  // T^T M and T^T (V^T B) in registers, then in place:  out[a][c] = sum_{k <= a} T[k][a] in[k][c].  T is stored with
+  // explicit zeros below the diagonal, so every loop below runs over all k with several independent accumulation
+  // chains per thread (the triangular, one-chain-at-a-time version was latency bound: 70 us per CTA)
+  double tm[4] = {0.0, 0.0, 0.0, 0.0}, tz[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) tz[u] = 0.0;
   {
+    const int z = tid & 127, hg = tid >> 7;
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+      const double mv = TM[k * (NB + 1) + lane];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int ar = wid + 8 * u;
-      double s = 0.0;
-      for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], TM[k * (NB + 1) + lane], s);
-      tm[u] = s;
-    }
-    if (hz) {
-      const int z = tid & 127, hg = tid >> 7;
+      for (int u = 0; u < 4; ++u) tm[u] = fma(Ts[k * (NB + 1) + wid + 8 * u], mv, tm[u]);
+      if (hz) {
+        const double zv = TZ[k * SY_ZW + z];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int ar = hg + 2 * u;
-        double s = 0.0;
-        for (int k = 0; k <= ar; ++k) s = fma(Ts[k * (NB + 1) + ar], TZ[k * SY_ZW + z], s);
-        tz[u] = s;
+        for (int u = 0; u < 16; ++u) tz[u] = fma(Ts[k * (NB + 1) + hg + 2 * u], zv, tz[u]);
       }
     }
   }
@@ -757,47 +756,62 @@ __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
     for (int u = 0; u < 16; ++u) TZ[(hg + 2 * u) * SY_ZW + z] = tz[u];
   }
   __syncthreads();
-  // X1 = Y - 1/2 V TM   (rows wid + 8 q)
+  // X1 = Y - 1/2 V TM   (rows wid + 8 q, 8 independent chains)
   double x1[WF_BM / 8];
 #pragma unroll
-  for (int q = 0; q < WF_BM / 8; ++q) {
-    const int rl = wid + 8 * q;
-    double s = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < NB; ++k) s = fma(Vs[rl * (NB + 1) + k], TM[k * (NB + 1) + lane], s);
-    x1[q] = Xs[rl * (NB + 1) + lane] - 0.5 * s;
+  for (int q = 0; q < WF_BM / 8; ++q) x1[q] = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < NB; ++k) {
+    const double tv = TM[k * (NB + 1) + lane];
+#pragma unroll
+    for (int q = 0; q < WF_BM / 8; ++q) x1[q] = fma(Vs[(wid + 8 * q) * (NB + 1) + k], tv, x1[q]);
   }
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) x1[q] = Xs[(wid + 8 * q) * (NB + 1) + lane] - 0.5 * x1[q];
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < WF_BM / 8; ++q) Xs[(wid + 8 * q) * (NB + 1) + lane] = x1[q];
   __syncthreads();
-  // W = X1 T   (T upper triangular: k <= c)
+  // W = X1 T
+  {
+    double wv[WF_BM / 8];
 #pragma unroll
-  for (int q = 0; q < WF_BM / 8; ++q) {
-    const int rl = wid + 8 * q;
-    double s = 0.0;
-    for (int k = 0; k <= lane; ++k) s = fma(Xs[rl * (NB + 1) + k], Ts[k * (NB + 1) + lane], s);
-    if (i0 + rl < n) W[(size_t)(i0 + rl) * NB + lane] = s;
+    for (int q = 0; q < WF_BM / 8; ++q) wv[q] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+      const double tv = Ts[k * (NB + 1) + lane];
+#pragma unroll
+      for (int q = 0; q < WF_BM / 8; ++q) wv[q] = fma(Xs[(wid + 8 * q) * (NB + 1) + k], tv, wv[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < WF_BM / 8; ++q) {
+      const int rl = wid + 8 * q;
+      if (i0 + rl < n) W[(size_t)(i0 + rl) * NB + lane] = wv[q];
+    }
   }
   if (hz) {
     double* Bq = a.Bq + (size_t)t * n * a.ldb;
     const int z = tid & 127, hg = tid >> 7;
     if (z < a.nz) {
-      // batches of 8 rows: all loads in flight before the first store
+      // batches of 8 rows: all loads in flight before the first store, 8 independent chains
       for (int rb = 0; rb < WF_BM; rb += 16) {
-        double bv[8];
+        double bv[8], sv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + rb + hg + 2 * u;
           bv[u] = (i < n) ? Bq[(size_t)i * a.ldb + z] : 0.0;
+          sv[u] = 0.0;
+        }
+#pragma unroll 4
+        for (int k = 0; k < NB; ++k) {
+          const double zv = TZ[k * SY_ZW + z];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sv[u] = fma(Vs[(rb + hg + 2 * u) * (NB + 1) + k], zv, sv[u]);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int rl = rb + hg + 2 * u;
-          double s = 0.0;
-#pragma unroll 8
-          for (int k = 0; k < NB; ++k) s = fma(Vs[rl * (NB + 1) + k], TZ[k * SY_ZW + z], s);
-          if (i0 + rl < n) Bq[(size_t)(i0 + rl) * a.ldb + z] = bv[u] - s;
+          if (i0 + rl < n) Bq[(size_t)(i0 + rl) * a.ldb + z] = bv[u] - sv[u];
         }
       }
     }

@@ -11,6 +11,8 @@
 // band (2 NB sub-diagonals, 4.3 MB per matrix at n = 8192) stays in L2.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "internal.cuh"
 
 namespace chd {
@@ -169,6 +171,165 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
   }
 }
 
+// ---- CTA-per-sweep variant (default): the same pipeline, but a sweep is owned by a 4-warp CTA (thread = (row, one
+// of four 8-column slices) of the 32 x 32 blocks), which cuts the serial part of a hop -- the dense updates -- by ~4.
+// The lag between consecutive sweeps (2 hops + flag visibility) is what bounds the whole stage.
+constexpr int CC_THREADS = 128;
+constexpr int CC_PARTS = CC_THREADS / 32;
+constexpr int CC_W = CB / CC_PARTS;   // columns (or rows) per slice
+constexpr int CC_SMEM_DOUBLES = 2 * CB * CS_ + 4 * CB + CC_PARTS * CB;
+
+__global__ void __launch_bounds__(CC_THREADS) chase_cta_kernel(ChaseArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
+  const int t = blockIdx.y, n = a.n;
+  const int W = gridDim.x, w = blockIdx.x;
+  double* bw = a.bandW + (size_t)t * n * CLD;
+  int* prog = a.prog + (size_t)t * n;
+  double* D = smem;                    // CB x CS_
+  double* S = D + CB * CS_;            // CB x CS_
+  double* vs = S + CB * CS_;           // CB
+  double* ws = vs + CB;                // CB
+  double* v2s = ws + CB;               // CB
+  double* zs = v2s + CB;               // CB
+  double* red = zs + CB;               // CC_PARTS x CB
+  const int c0 = part * CC_W;          // this thread's column slice (row = lane) / row slice (column = lane)
+
+  for (int j = w; j <= n - 3; j += W) {
+    int lo = j + 1, hi = min(j + CB, n - 1);
+    int len = hi - lo + 1;
+    int h = 0;
+    auto wait_prev = [&](int need) {
+      if (j > 0 && tid == 0) {
+        unsigned long long spins = 0;
+        while (ld_acquire(prog + j - 1) < need)
+          if (++spins > (1ull << 26)) asm volatile("trap;");
+      }
+      __syncthreads();
+    };
+    wait_prev(2);
+    // first reflector of the sweep: column j, rows lo..hi (every warp computes it: lane = row)
+    double v, tau, beta;
+    {
+      const double x = (lane < len) ? __ldcg(bw + (size_t)(lo + lane) * CLD + (lane + 1)) : 0.0;
+      warp_reflector(x, lane, len, v, tau, beta);
+      if (part == 0 && lane < len) __stcg(bw + (size_t)(lo + lane) * CLD + (lane + 1), (lane == 0) ? beta : 0.0);
+    }
+    while (true) {
+      const int lo2 = hi + 1, hi2 = min(hi + CB, n - 1);
+      const int len2 = hi2 - lo2 + 1;
+      const int off = lo2 - lo;
+      // ---------------- loads: warp `part` fetches rows c0 .. c0 + CC_W - 1 of both blocks
+      double dr[CC_W], sr[CC_W];
+#pragma unroll
+      for (int i = 0; i < CC_W; ++i) {
+        const int l = c0 + i;
+        dr[i] = (l < len && lane <= l) ? __ldcg(bw + (size_t)(lo + l) * CLD + lane) : 0.0;
+        sr[i] = (l < len2 && lane < len) ? __ldcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane)) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < CC_W; ++i) {
+        const int l = c0 + i;
+        if (lane <= l) {
+          D[l * CS_ + (l - lane)] = dr[i];
+          D[(l - lane) * CS_ + l] = dr[i];
+        }
+        S[l * CS_ + lane] = sr[i];
+      }
+      if (part == 0) vs[lane] = v;
+      __syncthreads();
+      // ---------------- D <- H D H   (thread: row = lane, columns c0 .. c0 + CC_W - 1)
+      {
+        double pp = 0.0;
+#pragma unroll
+        for (int c = 0; c < CC_W; ++c) pp = fma(D[lane * CS_ + c0 + c], vs[c0 + c], pp);
+        red[part * CB + lane] = pp;
+      }
+      __syncthreads();
+      double p = 0.0;
+#pragma unroll
+      for (int q = 0; q < CC_PARTS; ++q) p += red[q * CB + lane];
+      p *= tau;
+      const double al = -0.5 * tau * warp_sum(p * v);
+      const double wv = p + al * v;
+      if (part == 0) ws[lane] = wv;
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < CC_W; ++c) D[lane * CS_ + c0 + c] -= v * ws[c0 + c] + wv * vs[c0 + c];
+      // ---------------- S <- S H
+      bool last = (len2 <= 0);
+      double v2 = 0.0, tau2 = 0.0;
+      {
+        double uu = 0.0;
+#pragma unroll
+        for (int c = 0; c < CC_W; ++c) uu = fma(S[lane * CS_ + c0 + c], vs[c0 + c], uu);
+        __syncthreads();                     // red[] of the D part consumed, D slices written
+        red[part * CB + lane] = uu;
+      }
+      // store D (rows c0 .. of this warp) while the S part goes on
+#pragma unroll
+      for (int i = 0; i < CC_W; ++i) {
+        const int l = c0 + i;
+        if (l < len && lane <= l) __stcg(bw + (size_t)(lo + l) * CLD + lane, D[l * CS_ + (l - lane)]);
+      }
+      __syncthreads();
+      if (!last) {
+        double u = 0.0;
+#pragma unroll
+        for (int q = 0; q < CC_PARTS; ++q) u += red[q * CB + lane];
+        u *= tau;
+#pragma unroll
+        for (int c = 0; c < CC_W; ++c) S[lane * CS_ + c0 + c] -= u * vs[c0 + c];
+        __syncthreads();
+        if (len2 >= 2) {
+          double beta2;
+          const double x = S[lane * CS_ + 0];
+          warp_reflector(x, lane, len2, v2, tau2, beta2);   // identical in every warp
+          __syncthreads();                   // everybody has read column 0
+          if (part == 0) {
+            v2s[lane] = v2;
+            S[lane * CS_ + 0] = (lane == 0) ? beta2 : 0.0;
+          }
+          __syncthreads();
+          // z[c] = tau2 sum_l v2[l] S[l][c]: thread (column = lane, rows c0 .. c0 + CC_W - 1)
+          {
+            double zz = 0.0;
+#pragma unroll
+            for (int i = 0; i < CC_W; ++i) zz = fma(v2s[c0 + i], S[(c0 + i) * CS_ + lane], zz);
+            red[part * CB + lane] = zz;
+          }
+          __syncthreads();
+          double z = 0.0;
+#pragma unroll
+          for (int q = 0; q < CC_PARTS; ++q) z += red[q * CB + lane];
+          z = (lane >= 1) ? z * tau2 : 0.0;
+#pragma unroll
+          for (int i = 0; i < CC_W; ++i) S[(c0 + i) * CS_ + lane] -= v2s[c0 + i] * z;
+        } else {
+          last = true;
+        }
+        // rows c0 .. of S were last written by this warp (left-apply) or, without it, by all warps (right-apply)
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < CC_W; ++i) {
+          const int l = c0 + i;
+          if (l < len2 && lane < len) __stcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane), S[l * CS_ + lane]);
+        }
+      }
+      // ---------------- publish progress, move on
+      __syncthreads();
+      ++h;
+      if (tid == 0) {
+        __threadfence();     // cumulative: the CTA's stores (ordered by the barrier) become visible before the flag
+        st_release(prog + j, last ? CH_DONE : h);
+      }
+      if (last) break;
+      v = v2; tau = tau2; lo = lo2; hi = hi2; len = len2;
+      wait_prev(h + 2);
+    }
+  }
+}
+
 __global__ void chase_extract_kernel(const double* __restrict__ bandW, int n, double* __restrict__ d,
                                      double* __restrict__ e) {
   const int t = blockIdx.y;
@@ -183,21 +344,27 @@ size_t chase_workspace(const Plan* pl, int T) { return align_up((size_t)T * pl->
 
 int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e, int T, cudaStream_t st) {
   const int n = pl->n;
-  const size_t smem = (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double);
+  static const int variant = getenv("CHD_CHASE") ? atoi(getenv("CHD_CHASE")) : 1;   // 0: one warp per sweep
+  const size_t smem = variant == 0 ? (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double)
+                                   : (size_t)CC_SMEM_DOUBLES * sizeof(double);
+  const int threads = variant == 0 ? CH_WARPS * 32 : CC_THREADS;
+  const int sweeps_per_cta = variant == 0 ? CH_WARPS : 1;
+  void* kfn = variant == 0 ? (void*)chase_kernel : (void*)chase_cta_kernel;
   static int max_ctas_per_sm = -1;
   if (max_ctas_per_sm < 0) {
-    CHD_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CHD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_kernel, CH_WARPS * 32, smem));
+    if (variant == 0) CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_kernel, threads, smem));
+    else CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_cta_kernel, threads, smem));
     max_ctas_per_sm = nb > 0 ? nb : 1;
   }
   if (n >= 3) {
     CHD_CUDA(cudaMemsetAsync(prog, 0, (size_t)T * n * sizeof(int), st));
-    // warps per matrix: all of them co-resident (the pipeline spins on its predecessors), at most the
+    // sweeps in flight per matrix: all of them co-resident (the pipeline spins on its predecessors), at most the
     // pipeline depth n / (2 NB)
     const int cap = pl->sm_count * max_ctas_per_sm;        // CTAs
     int per = cap / T;
-    const int want = (n / (2 * CB) + CH_WARPS) / CH_WARPS;
+    const int want = (n / (2 * CB) + sweeps_per_cta) / sweeps_per_cta;
     if (per > want) per = want;
     if (per < 1) per = 1;
     for (int t0 = 0; t0 < T; ) {
@@ -208,7 +375,7 @@ int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e,
       void* params[] = {&a};
       int prc;
       if ((prc = profile_mark_begin(PROF_CHASE, st))) return prc;
-      CHD_CUDA(cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(per, cnt), dim3(CH_WARPS * 32), params, smem, st));
+      CHD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(per, cnt), dim3(threads), params, smem, st));
       g_launches.fetch_add(1);
       if ((prc = profile_mark_end(PROF_CHASE, st))) return prc;
       t0 += cnt;
