@@ -358,7 +358,8 @@ def run_b200(args):
         except Exception:  # noqa: BLE001
             pass
         stage1_ms = sum(prof_main.get(k, (0.0, 0))[0] for k in ("symm", "syr2k", "panel_qr", "wform"))
-        roofline = {"kernel": f"{dom}_kernel (dense->band stage of the two-stage reduction, FP64 DMMA m8n8k4, "
+        kfull = {"symm": "symm_kernel", "syr2k": "syr2k_row_kernel"}[dom]
+        roofline = {"kernel": f"{kfull} (dense->band stage of the two-stage reduction, FP64 DMMA m8n8k4, "
                               f"batched over {Tb} targets per launch)",
                     "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "peak_source": peak_src,

@@ -179,7 +179,7 @@ constexpr int CC_PARTS = CC_THREADS / 32;
 constexpr int CC_W = CB / CC_PARTS;   // columns (or rows) per slice
 constexpr int CC_SMEM_DOUBLES = 2 * CB * CS_ + 4 * CB + CC_PARTS * CB;
 
-__global__ void __launch_bounds__(CC_THREADS) chase_cta_kernel(ChaseArgs a) {
+__global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
   const int t = blockIdx.y, n = a.n;

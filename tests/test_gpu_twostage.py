@@ -155,7 +155,7 @@ def test_band_solve_matches_dense_solve(n):
         assert abs(r["z_high"][t].item() - nz[95]) < 1e-10 * nz[95]
 
 
-@pytest.mark.parametrize("n,N", [(180, 6), (420, 6), (257, 9), (40, 5)])
+@pytest.mark.parametrize("n,N", [(180, 6), (420, 6), (257, 9), (40, 5), (21, 4), (1031, 5)])
 def test_regress_two_stage_matches_oracle(n, N):
     nat = _native()
     X, _ = _data(n, N, 8)
