@@ -294,8 +294,8 @@ constexpr int RG_XW = 2 * NB;
 __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
   __shared__ __align__(16) double xch[2 * QR_MAXCS * RG_XW];
   __shared__ double red[RG_NW * NB];
-  __shared__ double mine[RG_XW];
-  __shared__ double tot[RG_XW];
+  __shared__ double rowbuf[NB];
+  __shared__ double tots[2 * RG_XW];
   __shared__ double taus[NB];
   __shared__ double Gs[NB * QR_S];
   cg::cluster_group cluster = cg::this_cluster();
@@ -323,26 +323,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
   if (tid < NB) taus[tid] = 0.0;
 
   int par = 0;
-  auto exchange = [&]() {
-    __syncthreads();
-    if (CS == 1) {
-      if (tid < RG_XW) tot[tid] = mine[tid];
-    } else {
-      for (int e = tid; e < CS * RG_XW; e += RG_THREADS) {
-        const int dst = e / RG_XW, q = e % RG_XW;
-        double* remote = cluster.map_shared_rank(xch + (par * QR_MAXCS + g) * RG_XW, dst);
-        remote[q] = mine[q];
-      }
-      cluster.sync();
-      if (tid < RG_XW) {
-        double s = 0.0;
-        for (int q = 0; q < CS; ++q) s += xch[(par * QR_MAXCS + q) * RG_XW + tid];
-        tot[tid] = s;
-      }
-      par ^= 1;
-    }
-    __syncthreads();
-  };
   __syncthreads();
 
 #pragma unroll 1
@@ -390,19 +370,46 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
         t1 = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
       red[wid * NB + lane] = t1;
-      if (wid == 1) mine[NB + lane] = 0.0;        // row tc: zero unless this CTA owns it (owner overwrites below)
-      __syncthreads();
-      if (wid == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < RG_NW; ++w) s += red[w * NB + lane];
-        mine[(lane + tc) & (NB - 1)] = s;         // back to natural column indices
-      }
       if (valid && pr == tc) {
 #pragma unroll
-        for (int q = 0; q < NB; ++q) mine[NB + ((q + tc) & (NB - 1))] = P[q];
+        for (int q = 0; q < NB; ++q) rowbuf[(q + tc) & (NB - 1)] = P[q];   // row tc, natural column order
       }
-      exchange();
+      __syncthreads();
+      // 64 values per CTA go round the cluster: u[c] (threads 0..31) and row tc from its owner (threads 32..63);
+      // written straight into every CTA's slot, summed in fixed order after ONE cluster barrier
+      double* tot = tots + par * RG_XW;
+      if (tid < RG_XW) {
+        double val;
+        int slot;
+        if (tid < NB) {
+          double sum = 0.0;
+#pragma unroll
+          for (int w = 0; w < RG_NW; ++w) sum += red[w * NB + tid];
+          val = sum;
+          slot = (tid + tc) & (NB - 1);                // back to natural column indices
+        } else {
+          val = (g == tc / a.RP) ? rowbuf[tid - NB] : 0.0;
+          slot = tid;
+        }
+        if (CS == 1) {
+          tot[slot] = val;
+        } else {
+          for (int dst = 0; dst < CS; ++dst)
+            cluster.map_shared_rank(xch + (par * QR_MAXCS + g) * RG_XW, dst)[slot] = val;
+        }
+      }
+      if (CS == 1) {
+        __syncthreads();
+      } else {
+        cluster.sync();
+        if (tid < RG_XW) {
+          double sum = 0.0;
+          for (int q = 0; q < CS; ++q) sum += xch[(par * QR_MAXCS + q) * RG_XW + tid];
+          tot[tid] = sum;
+        }
+        __syncthreads();
+      }
+      par ^= 1;
       const double ssq = tot[tc], alpha = tot[NB + tc];
       double beta, tau, scale;
       if (ssq == 0.0) {
@@ -426,7 +433,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
         if (lane < tc) Gs[lane * QR_S + tc] = fma(scale, tot[lane], tot[NB + lane]);
         if (lane == 0) taus[tc] = tau;
       }
-      __syncthreads();   // tot[] consumed before the next exchange overwrites it
+      // no barrier here: tot is double buffered, red / rowbuf are rewritten only after this column's barriers
     }
     // rotate: the finished column moves to the end
     {
@@ -437,6 +444,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
     }
   }
 
+  __syncthreads();
   // ---- compact-WY factor (dlarft, forward columnwise): lane a owns row a of T
   if (wid == 0 && g == 0) {
     double Tr[NB];
