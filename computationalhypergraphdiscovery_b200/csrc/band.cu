@@ -477,12 +477,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
 }
 
 // ------------------------------------------------------------------ Y = A22 V
-constexpr int SY_BM = 128, SY_KC = 32;
-constexpr int SY_SD = SY_KC + 4;    // direct tile [i][k] stride (== 4 mod 8: conflict-free fragment loads)
+constexpr int SY_BM = 128;
 constexpr int SY_ST = SY_BM + 8;    // transposed tile [k][i] stride (== 8 mod 16)
 constexpr int SY_SV = NB + 8;       // V chunk [k][c] stride (== 8 mod 16)
-constexpr int SY_TILE = (SY_BM * SY_SD > SY_KC * SY_ST) ? SY_BM * SY_SD : SY_KC * SY_ST;
-constexpr int SY_STAGE = SY_TILE + SY_KC * SY_SV;
+// per k-chunk width KC (32: two CTAs per SM; 64: one CTA per SM, half the barriers per DMMA)
+template <int KC> struct SymmCfg {
+  static constexpr int SD = KC + 4;   // direct tile [i][k] stride (== 4 mod 8: conflict-free fragment loads)
+  static constexpr int TILE = (SY_BM * SD > KC * SY_ST) ? SY_BM * SD : KC * SY_ST;
+  static constexpr int STAGE = TILE + KC * SY_SV;
+};
 constexpr int SY_NST = 2;
 constexpr int SY_ZW = 128;          // padded width of the Z-block partials
 constexpr int SY_MAXSPLIT = 4;      // split-K factor of the symm (partial Y buffers)
@@ -500,19 +503,20 @@ struct SymmArgs {
 
 // one staged k-chunk (SY_KC columns) of the row block: direct tile [i][k], transposed tile [k][i], optionally
 // masked against the diagonal (only the chunks that cross it)
-template <bool TR, bool MK>
+template <bool TR, bool MK, int KC>
 __device__ __forceinline__ void symm_chunk(double (&acc)[2][4][2], const double* __restrict__ tile,
                                            const double* __restrict__ vs, int wid, int fr, int fk, int i0, int j0) {
-  const double* ap = TR ? tile + fk * SY_ST + 16 * wid + fr : tile + (16 * wid + fr) * SY_SD + fk;
+  constexpr int SD = SymmCfg<KC>::SD;
+  const double* ap = TR ? tile + fk * SY_ST + 16 * wid + fr : tile + (16 * wid + fr) * SD + fk;
   const double* vp = vs + fk * SY_SV + fr;
 #pragma unroll
-  for (int kk = 0; kk < SY_KC; kk += 4) {
+  for (int kk = 0; kk < KC; kk += 4) {
     double af[2], bf[4];
 #pragma unroll
     for (int y = 0; y < 4; ++y) bf[y] = vp[kk * SY_SV + y * 8];
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-      af[x] = TR ? ap[kk * SY_ST + 8 * x] : ap[8 * x * SY_SD + kk];
+      af[x] = TR ? ap[kk * SY_ST + 8 * x] : ap[8 * x * SD + kk];
       if (MK) {
         const int i = i0 + 16 * wid + 8 * x + fr, j = j0 + kk + fk;
         if (TR ? (j <= i) : (j > i)) af[x] = 0.0;
@@ -525,7 +529,9 @@ __device__ __forceinline__ void symm_chunk(double (&acc)[2][4][2], const double*
   }
 }
 
-__global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
+template <int KC>
+__global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a) {
+  constexpr int SY_KC = KC, SY_SD = SymmCfg<KC>::SD, SY_TILE = SymmCfg<KC>::TILE, SY_STAGE = SymmCfg<KC>::STAGE;
   extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.y, bx = blockIdx.x, sp = blockIdx.z, S = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -550,7 +556,9 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
     else { q = it - nd; tr = true; mk = false; }
   };
   // per-thread copy geometry (fixed over the loop)
-  const int drow = tid >> 4, dpart = tid & 15;    // direct tile: rows drow + 16 s, 16-byte chunk dpart
+  constexpr int DPR = KC / 2, DRS = 256 / DPR;    // 16-byte chunks per direct-tile row, rows per pass
+  const int drow = tid / DPR, dpart = tid % DPR;  // direct tile: rows drow + DRS s, 16-byte chunk dpart
+  const int vrow = tid >> 4, vpart = tid & 15;    // V chunk: rows vrow + 16 s
   const int trow = tid >> 6, tpart = tid & 63;    // transposed tile: rows trow + 4 s, chunk tpart
   const double* dsrc = A + (size_t)(i0 + drow) * ldk + 2 * dpart;
   const double* tsrc = A + (size_t)trow * ldk + i0 + 2 * tpart;
@@ -565,22 +573,22 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
     if (!tr) {
       const bool cok = j0 + 2 * dpart < n;
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const bool ok = cok && (i0 + drow + 16 * s < n);
-        cp_async16(tile + (drow + 16 * s) * SY_SD + 2 * dpart, ok ? dsrc + (size_t)16 * s * ldk + j0 : A, ok);
+      for (int s = 0; s < SY_BM / DRS; ++s) {
+        const bool ok = cok && (i0 + drow + DRS * s < n);
+        cp_async16(tile + (drow + DRS * s) * SY_SD + 2 * dpart, ok ? dsrc + (size_t)DRS * s * ldk + j0 : A, ok);
       }
     } else {
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
+      for (int s = 0; s < KC / 4; ++s) {
         const bool ok = tcol_ok && (j0 + trow + 4 * s < n);
         cp_async16(tile + (trow + 4 * s) * SY_ST + 2 * tpart, ok ? tsrc + (size_t)(j0 + 4 * s) * ldk : A, ok);
       }
     }
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int row = drow + 16 * s;
+    for (int s = 0; s < KC / 16; ++s) {
+      const int row = vrow + 16 * s;
       const bool ok = (j0 + row < n);
-      cp_async16(vs + row * SY_SV + 2 * dpart, ok ? V + (size_t)(j0 + row) * NB + 2 * dpart : V, ok);
+      cp_async16(vs + row * SY_SV + 2 * vpart, ok ? V + (size_t)(j0 + row) * NB + 2 * vpart : V, ok);
     }
   };
 
@@ -603,11 +611,11 @@ __global__ void __launch_bounds__(256, 2) symm_kernel(SymmArgs a) {
     const double* vs = tile + SY_TILE;
     const int j0 = r0 + SY_KC * q;
     if (!mk) {
-      if (!tr) symm_chunk<false, false>(acc, tile, vs, wid, fr, fk, i0, j0);
-      else symm_chunk<true, false>(acc, tile, vs, wid, fr, fk, i0, j0);
+      if (!tr) symm_chunk<false, false, KC>(acc, tile, vs, wid, fr, fk, i0, j0);
+      else symm_chunk<true, false, KC>(acc, tile, vs, wid, fr, fk, i0, j0);
     } else {
-      if (!tr) symm_chunk<false, true>(acc, tile, vs, wid, fr, fk, i0, j0);
-      else symm_chunk<true, true>(acc, tile, vs, wid, fr, fk, i0, j0);
+      if (!tr) symm_chunk<false, true, KC>(acc, tile, vs, wid, fr, fk, i0, j0);
+      else symm_chunk<true, true, KC>(acc, tile, vs, wid, fr, fk, i0, j0);
     }
     __syncthreads();
   }
@@ -1265,15 +1273,19 @@ static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B,
   int S = 1;
   {
     const int slots = 2 * pl->sm_count;
-    const int niter_min = (m + SY_KC - 1) / SY_KC;
+    const int niter_min = (m + 31) / 32;
     while (S < SY_MAXSPLIT && nblk * T * S < 2 * slots && niter_min / (2 * S) >= 4) S *= 2;
   }
   {
     SymmArgs a;
     a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Y = bb.Y; a.Bq = B; a.ldb = ldb; a.nz = nz;
     a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk * S; a.nzblk = nblk;
+    static const int kc = getenv("CHD_SYMM_KC") ? atoi(getenv("CHD_SYMM_KC")) : 32;
     if ((rc = profile_mark_begin(PROF_SYMM, st))) return rc;
-    symm_kernel<<<dim3(nblk, T, S), 256, SY_NST * SY_STAGE * sizeof(double), st>>>(a);
+    if (kc == 64)
+      symm_kernel<64><<<dim3(nblk, T, S), 256, SY_NST * SymmCfg<64>::STAGE * sizeof(double), st>>>(a);
+    else
+      symm_kernel<32><<<dim3(nblk, T, S), 256, SY_NST * SymmCfg<32>::STAGE * sizeof(double), st>>>(a);
     CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
   }
@@ -1328,8 +1340,10 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
   if (nz > SY_ZW || (ldk & 1)) return CHD_EINVAL;
   static bool attr_set = false;
   if (!attr_set) {
-    CHD_CUDA(cudaFuncSetAttribute(symm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(SY_NST * SY_STAGE * sizeof(double))));
+    CHD_CUDA(cudaFuncSetAttribute(symm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SY_NST * SymmCfg<32>::STAGE * sizeof(double))));
+    CHD_CUDA(cudaFuncSetAttribute(symm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SY_NST * SymmCfg<64>::STAGE * sizeof(double))));
     CHD_CUDA(cudaFuncSetAttribute(syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)((S2_BM + S2_BN) * S2_S * sizeof(double))));
     CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
