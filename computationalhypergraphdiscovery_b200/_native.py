@@ -330,7 +330,7 @@ class Plan:
     def predict(self, desc, X, Xq, w, yb):
         T, nq = w.shape[0], Xq.shape[0]
         out = torch.empty((T, nq), dtype=torch.float64, device=self.device)
-        need = self.workspace_bytes(T) + T * nq * self.ldk * 8 + nq * 8 * ((self.N + 15) // 16 * 16) * T + 4096
+        need = self.workspace_bytes(T) + T * nq * self.ldk * 8 + nq * 8 * ((self.N + 31) // 32 * 32) * T + 4096
         ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         _check(load().chd_predict(self._h, ctypes.byref(desc), _ptr(X), _ptr(Xq), nq, _ptr(w), _ptr(yb), T, _ptr(out),
                                   _ptr(ws), ws.numel(), _stream()), "chd_predict")

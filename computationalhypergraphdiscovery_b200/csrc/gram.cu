@@ -1,7 +1,7 @@
 // Mode-kernel (Gram) matrix assembly.
 //   compact_kernel : per-target list of active variable indices (gather instead of the
 //                    reference's multiply-by-mask; adds exact zeros only).
-//   gather_kernel  : Xc[t] = X[:, active]  (n x ldp, zero padded to a multiple of 16 columns)
+//   gather_kernel  : Xc[t] = X[:, active]  (n x ldp, zero padded to a multiple of GK = 32 columns)
 //   gram_kernel    : L = Xq_c Xc^T on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4) with the
 //                    polynomial / product-of-RBF map fused into the k-loop + epilogue:
 //                      linear    1 + s L                              (Modes/kernels.py:99-102)
@@ -44,13 +44,13 @@ __global__ void gather_kernel(const double* __restrict__ X, int n, int N, const 
 }
 
 constexpr int GT = 64;        // CTA tile (GT x GT)
-constexpr int GK = 16;        // k chunk
-constexpr int GS = GK + 4;    // smem row stride (== 4 mod 16 -> conflict-free DMMA fragment loads)
+constexpr int GK = 32;        // k chunk
+constexpr int GS = GK + 4;    // smem row stride (== 4 mod 8 -> conflict-free DMMA fragment loads)
 
 // A = rows of Xq_c (nq x ldp), B = rows of Xc (n x ldp).  K[t] is nq x ldk.
 // SYMM: Xq == X, only tiles with bi >= bj are computed and mirrored.
 template <bool SYMM>
-__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ XcA, const double* __restrict__ XcB,
+__global__ void __launch_bounds__(256, 2) gram_kernel(const double* __restrict__ XcA, const double* __restrict__ XcB,
                                                    int nq, int n, int ldp, const int32_t* __restrict__ pcount,
                                                    double* __restrict__ K, int ldk, chd_kernel_desc kd,
                                                    double* __restrict__ P, int pmode,
@@ -99,19 +99,32 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
   const double inv2l2 = gauss ? 1.0 / (2.0 * kd.l * kd.l) : 0.0;
 
   const int kend = (p + GK - 1) / GK * GK;
-  for (int k0 = 0; k0 < kend; k0 += GK) {
-    // stage tiles (64 rows x 16 k) : 512 double2 per operand, 256 threads -> 2 each per operand
+  // tiles of 64 rows x 32 k: 1024 double2 per operand, 4 per thread; the next chunk is fetched into registers
+  // while the current one is on the tensor cores
+  double2 pa[4], pb[4];
+  auto gload = [&](const double* __restrict__ SA, const double* __restrict__ SB, int k0) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      int id = tid + s * 256;
-      int r = id >> 3, c2 = id & 7;
-      double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-      if (row0 + r < nq) va = *reinterpret_cast<const double2*>(A + (size_t)(row0 + r) * ldp + k0 + 2 * c2);
-      if (col0 + r < n) vb = *reinterpret_cast<const double2*>(B + (size_t)(col0 + r) * ldp + k0 + 2 * c2);
-      *reinterpret_cast<double2*>(&As[r * GS + 2 * c2]) = va;
-      *reinterpret_cast<double2*>(&Bs[r * GS + 2 * c2]) = vb;
+    for (int s = 0; s < 4; ++s) {
+      const int id = tid + s * 256, r = id >> 4, c2 = id & 15;
+      pa[s] = (row0 + r < nq) ? *reinterpret_cast<const double2*>(SA + (size_t)(row0 + r) * ldp + k0 + 2 * c2)
+                              : make_double2(0.0, 0.0);
+      pb[s] = (col0 + r < n) ? *reinterpret_cast<const double2*>(SB + (size_t)(col0 + r) * ldp + k0 + 2 * c2)
+                             : make_double2(0.0, 0.0);
     }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int id = tid + s * 256, r = id >> 4, c2 = id & 15;
+      *reinterpret_cast<double2*>(&As[r * GS + 2 * c2]) = pa[s];
+      *reinterpret_cast<double2*>(&Bs[r * GS + 2 * c2]) = pb[s];
+    }
+  };
+  if (kend > 0) gload(A, B, 0);
+  for (int k0 = 0; k0 < kend; k0 += GK) {
+    sstore();
     __syncthreads();
+    if (k0 + GK < kend) gload(A, B, k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; kk += 4) {
       double af[4], bf[2];
@@ -154,16 +167,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ Xc
     const int pr = rcount[t];
     const double* R = Xr + (size_t)t * n * ldp;
     for (int k0 = 0; k0 < pr; k0 += GK) {
-#pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        int id = tid + s2 * 256;
-        int r = id >> 3, c2 = id & 7;
-        double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-        if (row0 + r < nq) va = *reinterpret_cast<const double2*>(R + (size_t)(row0 + r) * ldp + k0 + 2 * c2);
-        if (col0 + r < n) vb = *reinterpret_cast<const double2*>(R + (size_t)(col0 + r) * ldp + k0 + 2 * c2);
-        *reinterpret_cast<double2*>(&As[r * GS + 2 * c2]) = va;
-        *reinterpret_cast<double2*>(&Bs[r * GS + 2 * c2]) = vb;
-      }
+      gload(R, R, k0);
+      sstore();
       __syncthreads();
       const int dmax = min(GK, pr - k0);
       for (int dd = 0; dd < dmax; ++dd) {
