@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s += P[a][b] * (1.0 - __drcp_rn(F[a][b]));   // F >= 1: IEEE reciprocal, no slow path
+        for (int b = 0; b < 4; ++b) s += P[a][b] * (1.0 - rcp_ge1(F[a][b]));
       s = warp_sum(s);
       if (lane == 0) sacc[c * 8 + wid] += s;
     }

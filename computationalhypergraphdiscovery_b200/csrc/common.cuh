@@ -98,7 +98,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // ---- exp(x) for x <= 0 (the RBF factors of the Gaussian mode): x = (64 q + j) ln2/64 + r, |r| <= ln2/128,
 // exp(x) = 2^q * 2^(j/64) * (1 + r + ... + r^5/120).  ~17 instructions instead of libdevice's ~40; max error
 // < 2 ulp (the truncation term r^6/720 is below 4e-17).  `tab` = 64 correctly rounded values of 2^(j/64) in shared
-// memory (exp_table_load).
+// memory (exp_table_load).  Arguments below -700 are clamped (result 1e-304 instead of 0).
 static __device__ const double g_exp2_tab[64] = {
     0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
     0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
@@ -123,7 +123,7 @@ __device__ __forceinline__ void exp_table_load(double* tab) {
 }
 
 __device__ __forceinline__ double exp_nonpos(double x, const double* __restrict__ tab) {
-  x = fmax(x, -800.0);
+  x = fmax(x, -700.0);      // exp(-700) = 1e-304 stands in for everything smaller (added to 1 by every caller)
   const double t = fma(x, 0x1.71547652b82fep+6, 0x1.8p+52);     // x * 64/ln2, rounded to an integer in the low bits
   const int k = __double2loint(t);
   const double kd = t - 0x1.8p+52;
@@ -136,8 +136,18 @@ __device__ __forceinline__ double exp_nonpos(double x, const double* __restrict_
   p = fma(p, r, 1.0);
   const int q = k >> 6;
   const double s = tab[k & 63] * p;
-  const double res = __hiloint2double(__double2hiint(s) + (q << 20), __double2loint(s));
-  return (q < -1000) ? 0.0 : res;
+  return __hiloint2double(__double2hiint(s) + (q << 20), __double2loint(s));   // q >= -1010: stays normal
+}
+
+// 1/f for f >= 1 (finite): hardware reciprocal seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (-> 2^-80):
+// 5 instructions instead of the ~12 of the IEEE-rounded __drcp_rn; error < 1 ulp.
+__device__ __forceinline__ double rcp_ge1(double f) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(f));
+  double e = fma(-f, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-f, r, 1.0);
+  return fma(r, e, r);
 }
 
 }  // namespace chd

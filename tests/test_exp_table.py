@@ -46,7 +46,7 @@ def test_scheme_is_within_two_ulp():
     assert abs(c5 - 1 / 120) < 1e-17 and abs(c4 - 1 / 24) < 1e-17 and abs(c3 - 1 / 6) < 1e-16
 
     def expn(x):
-        x = max(x, -800.0)
+        x = max(x, -700.0)
         k = int(np.rint(x * l2e64))
         kd = float(k)
         r = (x - kd * hi) - kd * lo
@@ -56,7 +56,7 @@ def test_scheme_is_within_two_ulp():
         p = p * r + 1.0
         p = p * r + 1.0
         q, j = k >> 6, k & 63
-        return tab[j] * p * 2.0 ** q if q >= -1000 else 0.0
+        return tab[j] * p * 2.0 ** q
 
     rng = np.random.default_rng(0)
     xs = -np.abs(rng.standard_normal(100000)) * rng.choice([1e-3, 0.1, 1.0, 10.0, 100.0], 100000)
@@ -66,4 +66,4 @@ def test_scheme_is_within_two_ulp():
         if ref > 1e-300:
             worst = max(worst, abs(expn(x) - ref) / math.ulp(ref))
     assert worst <= 2.0, worst
-    assert expn(0.0) == 1.0 and expn(-1e9) == 0.0
+    assert expn(0.0) == 1.0 and 0.0 < expn(-1e9) < 1e-300
