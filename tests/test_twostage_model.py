@@ -78,3 +78,19 @@ def test_twostage_ragged_sizes(n, b):
     F1 = ga @ np.linalg.solve(K + g * np.eye(n), ga)
     eta, _, _ = tm.eta_jets(d, np.r_[e, 0.0], g)
     assert abs(s1["beta0"] ** 2 / eta - F1) < 1e-11 * abs(F1)
+
+
+@pytest.mark.parametrize("m,b", [(200, 32), (40, 32), (33, 32), (20, 32), (2, 32), (64, 8)])
+def test_one_exchange_panel_qr_equals_householder_qr(m, b):
+    """The single-reduction-per-column formulation of the CUDA panel QR equals the textbook Householder QR."""
+    rng = np.random.default_rng(m)
+    P = rng.standard_normal((m, b))
+    R1, V1, tau1, T1 = ts.panel_qr(P)
+    R2, V2, tau2, T2 = ts.panel_qr_one_exchange(P)
+    np.testing.assert_allclose(tau2, tau1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(V2, V1, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(R2, R1, rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(T2, T1, rtol=1e-10, atol=1e-12)
+    Q = np.eye(m) - V2 @ T2 @ V2.T
+    np.testing.assert_allclose(Q.T @ Q, np.eye(m), atol=1e-12)
+    np.testing.assert_allclose(Q.T @ P, R2, atol=1e-11)

@@ -189,3 +189,48 @@ def band_solve(L, R):
                 z[i] = z[i] - L[i + p, p] * z[i + p]
         z[i] = z[i] / L[i, 0]
     return y, z
+
+
+def panel_qr_one_exchange(P):
+    """The formulation panel_qr_reg_kernel (csrc/band.cu) uses: per column ONE reduction over the rows -- the unscaled
+    products u[c] = sum_{r > t} x_r P[r, c] (x = column t) for ALL columns c, next to row t itself.  u[t] is the
+    squared norm the reflector needs, u[c > t] gives v^T P through  w_c = tau (P[t, c] + scale u[c]),  and u[c < t]
+    gives the Gram entries  v_c . v_t = V[t, c] + scale u[c]  of the compact-WY factor (the finished columns hold
+    their reflectors in place).  Returns what panel_qr returns."""
+    m, b = P.shape
+    P = P.copy()
+    tau = np.zeros(b)
+    G = np.zeros((b, b))
+    nref = min(b, m - 1)
+    for t in range(nref):
+        x = P[:, t].copy()
+        x[:t + 1] = 0.0
+        u = x @ P                      # the one reduction (all b columns)
+        row = P[t].copy()              # from the owner of row t
+        ssq, alpha = u[t], row[t]
+        if ssq == 0.0:
+            beta, tau[t], scale = alpha, 0.0, 0.0
+        else:
+            beta = -np.copysign(np.sqrt(alpha * alpha + ssq), alpha)
+            tau[t] = (beta - alpha) / beta
+            scale = 1.0 / (alpha - beta)
+        v = x * scale
+        v[t] = 1.0
+        w = tau[t] * (row + scale * u)
+        P[t:, t + 1:] -= np.outer(v[t:], w[t + 1:])
+        G[:t, t] = row[:t] + scale * u[:t]
+        P[t, t] = beta
+        P[t + 1:, t] = v[t + 1:]
+    V = np.tril(P[:, :b], -1)
+    V[:, nref:] = 0.0
+    for t in range(nref):
+        V[t, t] = 1.0
+    T = np.zeros((b, b))
+    for t in range(b):
+        T[t, t] = tau[t]
+        if t:
+            T[:t, t] = -tau[t] * (T[:t, :t] @ G[:t, t])
+    R = np.triu(P[:, :b]) if m >= b else np.triu(P)
+    Rfull = np.zeros_like(P)
+    Rfull[:R.shape[0]] = R[:m]
+    return Rfull, V, tau, T
