@@ -94,3 +94,22 @@ def test_one_exchange_panel_qr_equals_householder_qr(m, b):
     Q = np.eye(m) - V2 @ T2 @ V2.T
     np.testing.assert_allclose(Q.T @ Q, np.eye(m), atol=1e-12)
     np.testing.assert_allclose(Q.T @ P, R2, atol=1e-11)
+
+
+@pytest.mark.parametrize("n,b", [(60, 8), (40, 32), (33, 32), (5, 4)])
+def test_band_ldl_equals_dense_solve(n, b):
+    """The square-root-free banded factorisation of bandsolve.cu, incl. an indefinite shift (negative pivots)."""
+    rng = np.random.default_rng(n)
+    band = np.zeros((n, b + 1))
+    for d in range(min(b, n - 1) + 1):
+        band[d:, d] = rng.standard_normal(n - d) * (2.0 if d == 0 else 0.3)
+    A = ts.band_to_dense(band)
+    R = rng.standard_normal((n, 7))
+    for g in (15.0, -0.37):
+        Lg = ts.band_ldl(band, g)
+        y, z = ts.band_ldl_solve(Lg, R)
+        ref = np.linalg.solve(A + g * np.eye(n), R)
+        np.testing.assert_allclose(z, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+        np.testing.assert_allclose(np.sum(y * y / Lg[:, :1], 0), np.sum(R * ref, 0), rtol=1e-8)
+        if g > 0:
+            assert (Lg[:, 0] > 0).all()

@@ -234,3 +234,46 @@ def panel_qr_one_exchange(P):
     Rfull = np.zeros_like(P)
     Rfull[:R.shape[0]] = R[:m]
     return Rfull, V, tau, T
+
+
+def band_ldl(band, g):
+    """The factorisation band_solve_kernel (csrc/bandsolve.cu) runs: T_b + g I = L D L^T, left-looking by columns,
+    no pivoting and no square roots (negative pivots pass through).  Returns Lg with Lg[i, 0] = D(i) and
+    Lg[i, d] = L(i, i-d) for d >= 1."""
+    n, b1 = band.shape
+    b = b1 - 1
+    Lg = np.zeros((n, b1))
+    for k in range(n):
+        # c_p = D(k-p) L(k, k-p)
+        c = np.zeros(b + 1)
+        for p in range(1, min(b, k) + 1):
+            c[p] = Lg[k - p, 0] * Lg[k, p]
+        s = np.zeros(b + 1)
+        for d in range(0, b + 1):
+            if k + d >= n:
+                break
+            s[d] = band[k + d, d] + (g if d == 0 else 0.0)
+            for p in range(1, min(b - d, k) + 1):
+                s[d] -= Lg[k + d, d + p] * c[p]
+        Lg[k, 0] = s[0]
+        for d in range(1, b + 1):
+            if k + d < n:
+                Lg[k + d, d] = s[d] / s[0]
+    return Lg
+
+
+def band_ldl_solve(Lg, R):
+    """(y, z) with L y = R and z = L^-T D^-1 y; then  R . z = sum y^2 / D  (the Z-test denominator)."""
+    n, b1 = Lg.shape
+    b = b1 - 1
+    y = np.array(R, dtype=np.float64, copy=True)
+    for i in range(n):
+        for p in range(1, min(b, i) + 1):
+            y[i] = y[i] - Lg[i, p] * y[i - p]
+    z = np.empty_like(y)
+    for i in range(n - 1, -1, -1):
+        z[i] = y[i] / Lg[i, 0]
+        for p in range(1, b + 1):
+            if i + p < n:
+                z[i] = z[i] - Lg[i + p, p] * z[i + p]
+    return y, z
