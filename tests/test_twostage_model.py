@@ -113,3 +113,17 @@ def test_band_ldl_equals_dense_solve(n, b):
         np.testing.assert_allclose(np.sum(y * y / Lg[:, :1], 0), np.sum(R * ref, 0), rtol=1e-8)
         if g > 0:
             assert (Lg[:, 0] > 0).all()
+
+
+@pytest.mark.parametrize("n,b,seed", [(40, 4, 0), (40, 4, 1), (70, 8, 2), (37, 8, 3), (30, 32, 4), (90, 32, 5)])
+def test_chase_pipeline_rule_is_sufficient(n, b, seed):
+    """The hop tasks of chase.cu, on the compact band storage, executed in a random order that respects only the
+    kernels' dependency rule (hop h of sweep j after hop h+1 of sweep j-1) give the sequential result."""
+    rng = np.random.default_rng(seed)
+    band = np.zeros((n, b + 1))
+    for d in range(min(b, n - 1) + 1):
+        band[d:, d] = rng.standard_normal(n - d) * (3.0 if d == 0 else 1.0)
+    d_seq, e_seq = ts.stage2(band)
+    d_par, e_par = ts.ChaseTasks(band).run(rng)
+    np.testing.assert_allclose(d_par, d_seq, rtol=0, atol=1e-11 * np.abs(d_seq).max())
+    np.testing.assert_allclose(np.abs(e_par), np.abs(e_seq), rtol=0, atol=1e-11 * np.abs(d_seq).max())

@@ -277,3 +277,91 @@ def band_ldl_solve(Lg, R):
             if i + p < n:
                 z[i] = z[i] - Lg[i + p, p] * z[i + p]
     return y, z
+
+
+class ChaseTasks:
+    """Stage 2 cut into the hop tasks the CUDA kernels run (csrc/chase.cu), on the same compact storage
+    (bw[i, d] = A(i, i-d), 2b sub-diagonals) and with the same dependency rule: hop h of sweep j may run once hop h-1
+    of sweep j and hop h+1 of sweep j-1 are done (or sweep j-1 has finished).  `run(order_rng)` executes the hops in a
+    RANDOM order that respects only that rule -- the result must not depend on the order."""
+
+    def __init__(self, band):
+        n, b1 = band.shape
+        self.n, self.b = n, b1 - 1
+        self.bw = np.zeros((n, 2 * self.b + 2))
+        self.bw[:, :b1] = band
+        self.state = {}      # sweep -> (h, lo, hi, v, tau) of its next hop, or None when finished
+        self.done = {}       # sweep -> hops finished (large when the sweep is over)
+
+    def A(self, r, c):
+        return self.bw[r, r - c] if r >= c else self.bw[c, c - r]
+
+    def setA(self, r, c, x):
+        if r >= c:
+            self.bw[r, r - c] = x
+        else:
+            self.bw[c, c - r] = x
+
+    def ready(self, j):
+        if j in self.done and self.done[j] >= 10 ** 9:
+            return False
+        h = self.state[j][0] if j in self.state else 0
+        return j == 0 or self.done.get(j - 1, 0) >= h + 2
+
+    def step(self, j):
+        n, b = self.n, self.b
+        if j not in self.state:                       # first reflector of the sweep
+            lo, hi = j + 1, min(j + b, n - 1)
+            x = np.array([self.A(r, j) for r in range(lo, hi + 1)])
+            v, tau, beta = reflector(x)
+            for i, r in enumerate(range(lo, hi + 1)):
+                self.setA(r, j, beta if i == 0 else 0.0)
+            self.state[j] = (0, lo, hi, v, tau)
+        h, lo, hi, v, tau = self.state[j]
+        I = list(range(lo, hi + 1))
+        D = np.array([[self.A(r, c) for c in I] for r in I])
+        p = tau * (D @ v)
+        p += (-0.5 * tau * (p @ v)) * v
+        D -= np.outer(v, p) + np.outer(p, v)
+        for a, r in enumerate(I):
+            for c_, c in enumerate(I):
+                if c <= r:
+                    self.setA(r, c, D[a, c_])
+        lo2, hi2 = hi + 1, min(hi + b, n - 1)
+        last = hi2 - lo2 + 1 <= 1
+        v2, tau2 = None, 0.0
+        if lo2 <= n - 1:
+            I2 = list(range(lo2, hi2 + 1))
+            S = np.array([[self.A(r, c) for c in I] for r in I2])
+            S -= tau * np.outer(S @ v, v)
+            if len(I2) >= 2:
+                v2, tau2, beta2 = reflector(S[:, 0].copy())
+                S[:, 0] = 0.0
+                S[0, 0] = beta2
+                S[:, 1:] -= tau2 * np.outer(v2, v2 @ S[:, 1:])
+            for a, r in enumerate(I2):
+                for c_, c in enumerate(I):
+                    self.setA(r, c, S[a, c_])
+        if last:
+            self.done[j] = 10 ** 9
+            self.state[j] = None
+        else:
+            self.done[j] = h + 1
+            self.state[j] = (h + 1, lo2, hi2, v2, tau2)
+
+    def run(self, rng):
+        n = self.n
+        sweeps = list(range(0, n - 2)) if self.b > 1 else []
+        started = 0
+        while True:
+            cand = [j for j in sweeps[:started + 1] if self.ready(j)]
+            if not cand:
+                if started + 1 < len(sweeps):
+                    started += 1
+                    continue
+                break
+            j = cand[int(rng.integers(len(cand)))]
+            self.step(j)
+            if j == sweeps[min(started, len(sweeps) - 1)] and started + 1 < len(sweeps):
+                started += 1
+        return self.bw[:, 0].copy(), self.bw[1:, 1].copy()
