@@ -156,11 +156,18 @@ class GraphDiscovery:
             self._cluster_of_d = torch.from_numpy(self.modes.cluster_of).to(dev)
         return self._plan
 
-    def _batch_size(self, T):
+    def _batch_size(self, T, chain_steps=0, gaussian=False):
+        """Targets per launch: one in-flight batch must fit in 70 % of the free device memory -- the library's
+        workspace, the Gram output (stage 1) or the Gaussian product-map cache (chain), and the per-step chain
+        outputs (yb of every step is kept, like the reference's ybs, MAIN:651-657)."""
         plan = self._device()
         free, _total = torch.cuda.mem_get_info(plan.device)
-        held = plan._ws.numel() if plan._ws is not None else 0
-        per = plan.workspace_bytes(1) + 2 * 8 * plan.n * plan.ldk   # + Gram output / Gaussian product-map cache
+        held = (plan._ws.numel() if plan._ws is not None else 0) + getattr(self, "_held_bytes", 0)
+        per = plan.workspace_bytes(1) + 8 * plan.n * plan.ldk * (2 if gaussian or not chain_steps else 1)
+        per += 8 * (plan.n + len(self.modes.clusters) + 8) * max(int(chain_steps), 0)
+        forced = getattr(self, "_force_batch_size", None)        # test hook: exercise the multi-batch path
+        if forced:
+            return int(max(1, min(T, forced)))
         return int(max(1, min(T, (0.7 * (free + held)) // per)))
 
     # ------------------------------------------------------------------ fit
@@ -422,10 +429,38 @@ class GraphDiscovery:
         max_rows = int(nonempty0.sum(axis=1).max()) if Tk else 0
         if group_max_rows is not None:
             max_rows = max(max_rows, int(group_max_rows))
-        steps_planned = min(loop_number, max_rows) if loop_number > 0 else 0
+        # the reference checks `all masks empty` AFTER a step (MAIN:659-660): at least one step runs whenever
+        # loop_number > 0, even if every initial mask of the group is already empty
+        steps_planned = min(loop_number, max(1, max_rows)) if loop_number > 0 else 0
         self.print_func(f"Finding ancestors with kernel [{kernel}]: {steps_planned} steps x {Tk} targets {message}")
 
-        bs = self._batch_size(Tk)
+        gaussian = kernel.desc is not None and kernel.desc.kind == _native.KERNEL_GAUSSIAN
+        bs = self._batch_size(Tk, chain_steps=steps_planned, gaussian=gaussian)
+        # Chain outputs of the whole group; every batch writes its slice as soon as its launch is enqueued, so only
+        # one batch's scratch (workspace, product-map cache, per-step outputs) is alive at a time.
+        f64 = torch.float64
+        cap = steps_planned                                   # grows only in the degenerate extra-step case below
+        chain = dict(noise=torch.empty((Tk, cap), dtype=f64, device=dev), z_low=torch.empty((Tk, cap), dtype=f64, device=dev),
+                     z_high=torch.empty((Tk, cap), dtype=f64, device=dev), gamma=torch.empty((Tk, cap), dtype=f64, device=dev),
+                     pruned=torch.zeros((Tk, cap), dtype=torch.int32, device=dev),
+                     act=torch.empty((Tk, max(cap, 1), C), dtype=f64, device=dev))
+        yb_chain = torch.empty((Tk, cap + 1, n), dtype=f64, device=dev)
+        yb_chain[:, 0] = torch.from_numpy(np.ascontiguousarray(ybs_kernel)).to(dev)
+        self._held_bytes = sum(v.numel() * v.element_size() for v in chain.values()) + yb_chain.numel() * 8
+        # Gaussian mode: product map prod(1 + E_d) carried from step to step (one division per prune); ONE buffer of
+        # the batch size, reused by the batches (they run one after another) and invalidated in between
+        p_buf = torch.empty((min(bs, Tk), n, plan.ldk), dtype=f64, device=dev) if gaussian and steps_planned else None
+
+        def grow(extra):
+            nonlocal yb_chain, cap
+            for k, v in chain.items():
+                if k == "act" and cap == 0:
+                    continue
+                pad = torch.empty(v.shape[:1] + (extra,) + v.shape[2:], dtype=v.dtype, device=dev)
+                chain[k] = torch.cat([v, pad], dim=1)
+            yb_chain = torch.cat([yb_chain, torch.empty((Tk, extra, n), dtype=f64, device=dev)], dim=1)
+            cap += extra
+
         batches = []
         for s in range(0, Tk, bs):
             sl = slice(s, min(Tk, s + bs))
@@ -436,10 +471,7 @@ class GraphDiscovery:
                 yb=torch.from_numpy(np.ascontiguousarray(ybs_kernel[sl])).to(dev),
                 keys=torch.from_numpy(subkeys_kernel[sl].astype(np.uint32).view(np.int32).copy()).to(dev),
                 lmin=torch.from_numpy(np.ascontiguousarray(lambda_min_kernel[sl])).to(dev),
-                gmin=torch.full((tb,), 1e-9, dtype=torch.float64, device=dev), ga=ga[sl].contiguous(), outs=[],
-                # Gaussian mode: product map prod(1 + E_d) carried from step to step (one division per prune)
-                p_cache=(dict(P=torch.empty((tb, n, plan.ldk), dtype=torch.float64, device=dev), valid=0)
-                         if kernel.desc is not None and kernel.desc.kind == _native.KERNEL_GAUSSIAN else None)))
+                gmin=torch.full((tb,), 1e-9, dtype=torch.float64, device=dev), ga=ga[sl].contiguous()))
         done = 0
         if loop_number == 0:
             # MAIN:662-691: no prune step, but the activations of the full set are still needed
@@ -447,52 +479,50 @@ class GraphDiscovery:
                 if kernel.desc is None:
                     ybh, gah, alh = b["yb"].cpu().numpy(), b["ga"].cpu().numpy(), b["alive"].cpu().numpy()
                     w0b = w0[b["sl"]]
-                    b["act0"] = np.stack([self._custom_activations(kernel, ybh[t], gah[t], w0b[t], alh[t])
-                                          for t in range(w0b.shape[0])])[:, None, :]
-                    continue
-                act, _ = plan.activations(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"], b["yb"],
-                                          b["ga"], False)
-                b["act0"] = act.cpu().numpy()[:, None, :]
+                    act0 = torch.from_numpy(np.stack([self._custom_activations(kernel, ybh[t], gah[t], w0b[t], alh[t])
+                                                      for t in range(w0b.shape[0])])).to(dev)
+                else:
+                    act0, _ = plan.activations(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"], b["yb"],
+                                               b["ga"], False)
+                chain["act"][b["sl"], 0] = act0
         else:
-            def run(nsteps):
+            def run(first, nsteps):
                 for b in batches:
+                    sl = b["sl"]
                     if kernel.desc is None:
-                        b["outs"].append(self._custom_chain(kernel, b, w0[b["sl"]], done, nsteps))
-                        continue
-                    b["outs"].append(plan.prune_chain(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"],
-                                                      b["ga"], b["yb"], b["keys"], b["lmin"], b["gmin"], done, nsteps,
-                                                      keep_yb=True, p_cache=b["p_cache"]))
-            run(steps_planned)
+                        o = self._custom_chain(kernel, b, w0[sl], first, nsteps)
+                    else:
+                        pc = dict(P=p_buf[:sl.stop - sl.start], valid=0) if p_buf is not None else None
+                        o = plan.prune_chain(kernel.desc, self._Xd, self._cluster_of_d, b["w0"], b["alive"], b["ga"],
+                                             b["yb"], b["keys"], b["lmin"], b["gmin"], first, nsteps, keep_yb=True,
+                                             p_cache=pc)
+                    for k in ("noise", "z_low", "z_high", "gamma", "pruned", "act"):
+                        chain[k][sl, first:first + nsteps] = o[k]
+                    yb_chain[sl, first + 1:first + 1 + nsteps] = o["yb"]
+                    del o
+            run(0, steps_planned)
             done = steps_planned
             # The reference keeps stepping until every mask of the group is empty or L steps are done
             # (MAIN:659-660).  An empty row only wins the argmin in degenerate cases (activation > 2 or
             # NaN), so this loop normally does not run.
             while done < loop_number and any(
                     self._nonempty(w0[b["sl"]], b["alive"].cpu().numpy()).any() for b in batches):
-                run(1)
+                grow(1)
+                run(done, 1)
                 done += 1
         torch.cuda.synchronize(dev)
+        del p_buf
+        self._held_bytes = 0
 
         S = done
         noises = np.empty((Tk, S + 1)); zl = np.empty((Tk, S + 1)); zh = np.empty((Tk, S + 1)); gm = np.empty((Tk, S + 1))
         noises[:, 0], zl[:, 0], zh[:, 0], gm[:, 0] = noise_kernel, Z_low_kernel, Z_high_kernel, gammas_kernel
-        pruned = np.zeros((Tk, S), dtype=np.int64)
-        activations = np.empty((Tk, max(S, 1), C))
-        yb_chain = torch.empty((Tk, S + 1, n), dtype=torch.float64, device=dev)
-        yb_chain[:, 0] = torch.from_numpy(np.ascontiguousarray(ybs_kernel)).to(dev)
-        for b in batches:
-            sl = b["sl"]
-            if loop_number == 0:
-                activations[sl] = b["act0"]
-                continue
-            cat = lambda name: torch.cat([o[name] for o in b["outs"]], dim=1)  # noqa: E731
-            noises[sl, 1:] = cat("noise").cpu().numpy()
-            zl[sl, 1:] = cat("z_low").cpu().numpy()
-            zh[sl, 1:] = cat("z_high").cpu().numpy()
-            gm[sl, 1:] = cat("gamma").cpu().numpy()
-            pruned[sl] = cat("pruned").cpu().numpy()
-            activations[sl] = cat("act").cpu().numpy()
-            yb_chain[sl, 1:] = cat("yb")
+        noises[:, 1:] = chain["noise"].cpu().numpy()
+        zl[:, 1:] = chain["z_low"].cpu().numpy()
+        zh[:, 1:] = chain["z_high"].cpu().numpy()
+        gm[:, 1:] = chain["gamma"].cpu().numpy()
+        pruned = chain["pruned"].cpu().numpy().astype(np.int64)
+        activations = chain["act"].cpu().numpy()
         # chain of variable masks (T_k, S+1, N) from the pruned cluster indices
         active = np.empty((Tk, S + 1, N))
         alive_h = np.ones((Tk, C))

@@ -305,7 +305,7 @@ class Plan:
         p_cache: optional dict {"P": (T, n, ldk) tensor, "valid": 0/1} carrying the Gaussian product map."""
         T = w0.shape[0]
         dev, f64 = self.device, torch.float64
-        S = max(int(steps), 1)
+        S = max(int(steps), 0)          # steps == 0: zero-length chain outputs, nothing launched
         out = dict(pruned=torch.full((T, S), -1, dtype=torch.int32, device=dev),
                    noise=torch.empty((T, S), dtype=f64, device=dev), z_low=torch.empty((T, S), dtype=f64, device=dev),
                    z_high=torch.empty((T, S), dtype=f64, device=dev), gamma=torch.empty((T, S), dtype=f64, device=dev),

@@ -409,12 +409,6 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
     const int ntiles = tb * (tb + 1) / 2;
     nblk = ntiles < GA_BLOCKS ? ntiles : GA_BLOCKS;
     const size_t smem = (size_t)C * 8 * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-      CHD_CUDA(cudaFuncSetAttribute(gauss_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)pl->smem_optin));
-      attr_set = true;
-    }
     gauss_pairs_kernel<<<dim3(nblk, T), 256, smem, st>>>(XT, n, N, C, yb, w, mem_off, mem_idx,
                                                          1.0 / (2.0 * kd->l * kd->l), gpart, nblk, P, ldk);
     CHD_LAUNCHED();
@@ -422,6 +416,12 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
   act_finalize_kernel<<<T, 256, 0, st>>>(*kd, N, C, w, mem_off, mem_idx, gdot, quad ? rowq : nullptr, gpart, nblk,
                                          energy, alive, act, act_stride, prune, pruned, pruned_stride);
   CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+int act_device_init(Plan* pl) {
+  CHD_CUDA(cudaFuncSetAttribute(gauss_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)pl->smem_optin));
   return CHD_OK;
 }
 

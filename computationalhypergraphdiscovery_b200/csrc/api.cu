@@ -62,7 +62,7 @@ static bool regress_carve(const Plan* pl, int T, Carver& cv, RegressBuffers& rb)
   rb.loss = cv.take<double>((size_t)T * CHD_GRID_POINTS);
   if (pl->two_stage) {
     const bool ok = band_carve(pl, T, cv, rb.bb);
-    rb.prog = cv.take<int>((size_t)T * n + 64);
+    rb.prog = cv.take<int>(chase_prog_ints(pl, T));
     rb.Lg = cv.take<double>((size_t)T * n * CHD_BAND_LD);
     rb.gu = cv.take<double>(T);
     return ok && cv.ok;
@@ -221,6 +221,22 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
       const int Gfull = slots / pl->wave;
       if (Gfull > pl->G && Gfull <= pl->sm_count) pl->G = Gfull;
       (void)fits(pl->threads == 256 ? (per_cta < pl->smem_optin ? per_cta : pl->smem_optin) : pl->smem_optin);
+    }
+  }
+  // function attributes and occupancy figures are per device: set them on the plan's device, whatever the
+  // caller's current device is
+  {
+    int cur = 0;
+    CHD_CUDA(cudaGetDevice(&cur));
+    if (cur != device) CHD_CUDA(cudaSetDevice(device));
+    int rc = band_device_init(pl);
+    if (!rc) rc = chase_device_init(pl);
+    if (!rc) rc = tridiag_device_init(pl);
+    if (!rc) rc = act_device_init(pl);
+    if (cur != device) cudaSetDevice(cur);
+    if (rc) {
+      delete pl;
+      return rc;
     }
   }
   *plan = (chd_plan*)pl;
@@ -397,7 +413,7 @@ struct BandWs {
 static bool band_ws_carve(const Plan* pl, int T, void* ws, size_t bytes, BandWs& w) {
   Carver cv(ws, bytes);
   const bool ok = band_carve(pl, T, cv, w.bb);
-  w.prog = cv.take<int>((size_t)T * pl->n + 64);
+  w.prog = cv.take<int>(chase_prog_ints(pl, T));
   w.Lg = cv.take<double>((size_t)T * pl->n * CHD_BAND_LD);
   return ok && cv.ok;
 }

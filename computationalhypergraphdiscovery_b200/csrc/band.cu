@@ -1334,50 +1334,49 @@ static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B,
   return CHD_OK;
 }
 
+int band_device_init(Plan* pl) {
+  CHD_CUDA(cudaFuncSetAttribute(symm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(SY_NST * SymmCfg<32>::STAGE * sizeof(double))));
+  CHD_CUDA(cudaFuncSetAttribute(symm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(SY_NST * SymmCfg<64>::STAGE * sizeof(double))));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((S2_BM + S2_BN) * S2_S * sizeof(double))));
+  CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((S3_BM + 2 * 32) * S2_S * sizeof(double))));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((S3_BM + 2 * 64) * S2_S * sizeof(double))));
+  CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
+  CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CHD_CUDA(cudaFuncSetAttribute(backtransform2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)pl->smem_optin));
+  // largest cluster the register-resident panel QR may use: 16 (non-portable) when the device can co-schedule it
+  const char* e = getenv("CHD_QR_REG");     // tuning / test switch: 0 disables the register-resident kernel
+  if (e && atoi(e) == 0) {
+    pl->qr_reg_max_cs = 0;
+  } else {
+    pl->qr_reg_max_cs = 8;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(16, 1); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = 0;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, panel_qr_reg_kernel, &cfg) == cudaSuccess && nclusters > 0)
+      pl->qr_reg_max_cs = 16;
+    else
+      (void)cudaGetLastError();
+  }
+  return CHD_OK;
+}
+
 int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nz,
                        double* beta0, const BandBuffers& bb, cudaStream_t st) {
   const int n = pl->n;
   if (nz > SY_ZW || (ldk & 1)) return CHD_EINVAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CHD_CUDA(cudaFuncSetAttribute(symm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(SY_NST * SymmCfg<32>::STAGE * sizeof(double))));
-    CHD_CUDA(cudaFuncSetAttribute(symm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(SY_NST * SymmCfg<64>::STAGE * sizeof(double))));
-    CHD_CUDA(cudaFuncSetAttribute(syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((S2_BM + S2_BN) * S2_S * sizeof(double))));
-    CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
-    CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((S3_BM + 2 * 32) * S2_S * sizeof(double))));
-    CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((S3_BM + 2 * 64) * S2_S * sizeof(double))));
-    CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
-    CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    CHD_CUDA(cudaFuncSetAttribute(backtransform2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->smem_optin));
-    attr_set = true;
-  }
-  // largest cluster the register-resident panel QR may use: 16 (non-portable) when the device can co-schedule it
-  static int reg_max_cs = -1;
-  {
-    const char* e = getenv("CHD_QR_REG");     // tuning / test switch: 0 disables the register-resident kernel
-    if (e && atoi(e) == 0) reg_max_cs = 0;
-    else if (reg_max_cs <= 0) {
-      reg_max_cs = 8;
-      cudaLaunchConfig_t cfg = {};
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      cfg.gridDim = dim3(16, 1); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = 0;
-      int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, panel_qr_reg_kernel, &cfg) == cudaSuccess && nclusters > 0)
-        reg_max_cs = 16;
-      else
-        (void)cudaGetLastError();
-    }
-  }
+  const int reg_max_cs = pl->qr_reg_max_cs;
   const size_t strideA = (size_t)n * ldk;
   if (ldk > n) {
     zero_pad_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(K, strideA, ldk, n);

@@ -6,11 +6,12 @@
 // NumPy model: tests/twostage_model.py::stage2.
 //
 // Parallelisation: sweep j (annihilate column j below the sub-diagonal, chase the bulge to the bottom) is owned
-// by one warp; warps of a matrix take sweeps round-robin and run as a software pipeline: hop h of sweep j+1 may
-// start once sweep j has finished hop h+1 (progress counters in global memory, release/acquire).  The working
-// band (2 NB sub-diagonals, 4.3 MB per matrix at n = 8192) stays in L2.
-#include <cooperative_groups.h>
-
+// by one CTA (or warp); the CTAs of a matrix run as a software pipeline: hop h of sweep j+1 may start once sweep j
+// has finished hop h+1 (progress counters in global memory, release/acquire).  Sweeps are handed out by a
+// per-matrix TICKET counter (atomicAdd): the CTA that draws sweep j knows that every sweep < j is owned by a CTA
+// that is already running, so the wait chain always bottoms out at a running CTA -- no co-residency requirement,
+// no cooperative launch, any grid size, and the kernel can share the GPU with the GEMMs of another stream.  The
+// working band (2 NB sub-diagonals, 4.3 MB per matrix at n = 8192) stays in L2.
 #include <stdlib.h>
 
 #include "internal.cuh"
@@ -26,8 +27,11 @@ constexpr int CH_DONE = 1 << 30;
 struct ChaseArgs {
   double* bandW;   // T x n x CLD, bandW[i][d] = A(i, i-d)
   int* prog;       // T x n   hops finished by sweep j
+  int* ticket;     // T       next sweep to hand out
+  int* err;        // 1       set when a wait on the predecessor sweep timed out (results become NaN)
   int n;
 };
+constexpr unsigned long long CH_SPIN_LIMIT = 1ull << 26;
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -58,7 +62,6 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int t = blockIdx.y, n = a.n;
-  const int W = gridDim.x * CH_WARPS, w = blockIdx.x * CH_WARPS + wid;
   double* bw = a.bandW + (size_t)t * n * CLD;
   int* prog = a.prog + (size_t)t * n;
   double* D = smem + (size_t)wid * (2 * CB * CS_ + 3 * CB);   // CB x CS_
@@ -67,18 +70,28 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
   double* ws = vs + CB;                                       // CB
   double* v2s = ws + CB;                                      // CB
 
-  for (int j = w; j <= n - 3; j += W) {
+  while (true) {
+    int j = 0;
+    if (lane == 0) j = atomicAdd(a.ticket + t, 1);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j > n - 3) break;
     int lo = j + 1, hi = min(j + CB, n - 1);
     int len = hi - lo + 1;
     int h = 0;
+    bool dead = false;
     auto wait_prev = [&](int need) {
-      if (j == 0) return;
-      if (lane == 0) {
-        while (ld_acquire(prog + j - 1) < need) __nanosleep(40);
+      int ok = 1;
+      if (j > 0 && lane == 0) {
+        unsigned long long spins = 0;
+        while (ld_acquire(prog + j - 1) < need) {
+          __nanosleep(40);
+          if (++spins > CH_SPIN_LIMIT) { ok = 0; atomicExch(a.err, 1); break; }
+        }
       }
-      __syncwarp();
+      dead = !__shfl_sync(0xffffffffu, ok, 0);
     };
     wait_prev(2);
+    if (dead) { if (lane == 0) st_release(prog + j, CH_DONE); break; }
     // first reflector of the sweep: column j, rows lo..hi
     double v, tau, beta;
     {
@@ -167,7 +180,9 @@ __global__ void __launch_bounds__(CH_WARPS * 32) chase_kernel(ChaseArgs a) {
       if (last) break;
       v = v2; tau = tau2; lo = lo2; hi = hi2; len = len2;
       wait_prev(h + 2);
+      if (dead) { if (lane == 0) st_release(prog + j, CH_DONE); break; }
     }
+    if (dead) break;
   }
 }
 
@@ -183,9 +198,9 @@ __global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) 
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
   const int t = blockIdx.y, n = a.n;
-  const int W = gridDim.x, w = blockIdx.x;
   double* bw = a.bandW + (size_t)t * n * CLD;
   int* prog = a.prog + (size_t)t * n;
+  __shared__ int s_j, s_ok;
   double* D = smem;                    // CB x CS_
   double* S = D + CB * CS_;            // CB x CS_
   double* vs = S + CB * CS_;           // CB
@@ -195,19 +210,27 @@ __global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) 
   double* red = zs + CB;               // CC_PARTS x CB
   const int c0 = part * CC_W;          // this thread's column slice (row = lane) / row slice (column = lane)
 
-  for (int j = w; j <= n - 3; j += W) {
+  while (true) {
+    if (tid == 0) { s_j = atomicAdd(a.ticket + t, 1); s_ok = 1; }
+    __syncthreads();
+    const int j = s_j;
+    if (j > n - 3) break;
     int lo = j + 1, hi = min(j + CB, n - 1);
     int len = hi - lo + 1;
     int h = 0;
-    auto wait_prev = [&](int need) {
+    // returns false when the predecessor never got there (a bug or a dead context): flag it and let the host see
+    // NaN results instead of trapping the whole context
+    auto wait_prev = [&](int need) -> bool {
       if (j > 0 && tid == 0) {
         unsigned long long spins = 0;
         while (ld_acquire(prog + j - 1) < need)
-          if (++spins > (1ull << 26)) asm volatile("trap;");
+          if (++spins > CH_SPIN_LIMIT) { s_ok = 0; atomicExch(a.err, 1); break; }
       }
       __syncthreads();
+      return s_ok != 0;
     };
-    wait_prev(2);
+    bool alive = wait_prev(2);
+    if (!alive) { if (tid == 0) st_release(prog + j, CH_DONE); break; }
     // first reflector of the sweep: column j, rows lo..hi (every warp computes it: lane = row)
     double v, tau, beta;
     {
@@ -325,63 +348,81 @@ __global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) 
       }
       if (last) break;
       v = v2; tau = tau2; lo = lo2; hi = hi2; len = len2;
-      wait_prev(h + 2);
+      alive = wait_prev(h + 2);
+      if (!alive) { if (tid == 0) st_release(prog + j, CH_DONE); break; }
     }
+    if (!alive) break;
+    __syncthreads();   // s_j is rewritten by thread 0 at the top of the loop
   }
 }
 
-__global__ void chase_extract_kernel(const double* __restrict__ bandW, int n, double* __restrict__ d,
-                                     double* __restrict__ e) {
+__global__ void chase_extract_kernel(const double* __restrict__ bandW, int n, const int* __restrict__ err,
+                                     double* __restrict__ d, double* __restrict__ e) {
   const int t = blockIdx.y;
   const double* bw = bandW + (size_t)t * n * CLD;
+  // a timed-out sweep leaves the band half reduced: poison the result so that every consumer reports NaN
+  const double poison = (err && *err) ? __longlong_as_double(0x7ff8000000000000ll) : 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    d[(size_t)t * n + i] = bw[(size_t)i * CLD];
-    e[(size_t)t * n + i] = (i + 1 < n) ? bw[(size_t)(i + 1) * CLD + 1] : 0.0;
+    d[(size_t)t * n + i] = bw[(size_t)i * CLD] + poison;
+    e[(size_t)t * n + i] = ((i + 1 < n) ? bw[(size_t)(i + 1) * CLD + 1] : 0.0) + poison;
   }
 }
 
-size_t chase_workspace(const Plan* pl, int T) { return align_up((size_t)T * pl->n * sizeof(int), 256) + 256; }
+// progress counters (T x n) + ticket counters (T) + error flag, zeroed before every launch
+size_t chase_prog_ints(const Plan* pl, int T) { return (size_t)T * pl->n + (size_t)T + 64; }
+size_t chase_workspace(const Plan* pl, int T) { return align_up(chase_prog_ints(pl, T) * sizeof(int), 256) + 256; }
+
+int chase_device_init(Plan* pl) {
+  const int variant = getenv("CHD_CHASE") ? atoi(getenv("CHD_CHASE")) : 1;   // 0: one warp per sweep
+  pl->chase_variant = variant;
+  const size_t smem = variant == 0 ? (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double)
+                                   : (size_t)CC_SMEM_DOUBLES * sizeof(double);
+  const int threads = variant == 0 ? CH_WARPS * 32 : CC_THREADS;
+  int nb = 0;
+  if (variant == 0) {
+    CHD_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_kernel, threads, smem));
+  } else {
+    CHD_CUDA(cudaFuncSetAttribute(chase_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_cta_kernel, threads, smem));
+  }
+  pl->chase_ctas_per_sm = nb > 0 ? nb : 1;
+  if (const char* e = getenv("CHD_CHASE_CTAS_PER_SM")) {   // tuning: leave room for another stream's kernels
+    const int v = atoi(e);
+    if (v >= 1 && v < pl->chase_ctas_per_sm) pl->chase_ctas_per_sm = v;
+  }
+  return CHD_OK;
+}
 
 int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e, int T, cudaStream_t st) {
   const int n = pl->n;
-  static const int variant = getenv("CHD_CHASE") ? atoi(getenv("CHD_CHASE")) : 1;   // 0: one warp per sweep
+  const int variant = pl->chase_variant;
   const size_t smem = variant == 0 ? (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double)
                                    : (size_t)CC_SMEM_DOUBLES * sizeof(double);
   const int threads = variant == 0 ? CH_WARPS * 32 : CC_THREADS;
   const int sweeps_per_cta = variant == 0 ? CH_WARPS : 1;
-  void* kfn = variant == 0 ? (void*)chase_kernel : (void*)chase_cta_kernel;
-  static int max_ctas_per_sm = -1;
-  if (max_ctas_per_sm < 0) {
-    CHD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    if (variant == 0) CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_kernel, threads, smem));
-    else CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_cta_kernel, threads, smem));
-    max_ctas_per_sm = nb > 0 ? nb : 1;
-  }
+  int* ticket = prog + (size_t)T * n;
+  int* err = ticket + T;
   if (n >= 3) {
-    CHD_CUDA(cudaMemsetAsync(prog, 0, (size_t)T * n * sizeof(int), st));
-    // sweeps in flight per matrix: all of them co-resident (the pipeline spins on its predecessors), at most the
-    // pipeline depth n / (2 NB)
-    const int cap = pl->sm_count * max_ctas_per_sm;        // CTAs
+    CHD_CUDA(cudaMemsetAsync(prog, 0, chase_prog_ints(pl, T) * sizeof(int), st));
+    // sweeps in flight per matrix: what fits on the device for all T matrices at once, at most the pipeline depth
+    // n / (2 NB).  One launch: sweeps are drawn from the ticket counters, so CTAs that are not resident yet are
+    // never waited for.
+    const int cap = pl->sm_count * pl->chase_ctas_per_sm;        // CTAs
     int per = cap / T;
     const int want = (n / (2 * CB) + sweeps_per_cta) / sweeps_per_cta;
     if (per > want) per = want;
     if (per < 1) per = 1;
-    for (int t0 = 0; t0 < T; ) {
-      int cnt = cap / per;
-      if (cnt > T - t0) cnt = T - t0;
-      ChaseArgs a;
-      a.bandW = bandW + (size_t)t0 * n * CLD; a.prog = prog + (size_t)t0 * n; a.n = n;
-      void* params[] = {&a};
-      int prc;
-      if ((prc = profile_mark_begin(PROF_CHASE, st))) return prc;
-      CHD_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(per, cnt), dim3(threads), params, smem, st));
-      g_launches.fetch_add(1);
-      if ((prc = profile_mark_end(PROF_CHASE, st))) return prc;
-      t0 += cnt;
-    }
+    ChaseArgs a;
+    a.bandW = bandW; a.prog = prog; a.ticket = ticket; a.err = err; a.n = n;
+    int prc;
+    if ((prc = profile_mark_begin(PROF_CHASE, st))) return prc;
+    if (variant == 0) chase_kernel<<<dim3(per, T), threads, smem, st>>>(a);
+    else chase_cta_kernel<<<dim3(per, T), threads, smem, st>>>(a);
+    CHD_LAUNCHED();
+    if ((prc = profile_mark_end(PROF_CHASE, st))) return prc;
   }
-  chase_extract_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(bandW, n, d, e);
+  chase_extract_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(bandW, n, n >= 3 ? err : nullptr, d, e);
   CHD_LAUNCHED();
   return CHD_OK;
 }

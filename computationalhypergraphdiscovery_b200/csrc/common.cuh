@@ -40,6 +40,10 @@ struct Plan {
   int rows_per_chunk;
   int two_stage;  // 1: dense -> band -> tridiagonal (band.cu / chase.cu / bandsolve.cu), 0: one-stage tridiag.cu
   size_t smem_optin;
+  // per-device results of the *_device_init calls of chd_plan_create (function attributes are per device)
+  int chase_variant;       // 1: CTA per sweep (default), 0: warp per sweep
+  int chase_ctas_per_sm;   // resident bulge-chasing CTAs per SM
+  int qr_reg_max_cs;       // largest cluster of the register-resident panel QR (0: disabled)
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

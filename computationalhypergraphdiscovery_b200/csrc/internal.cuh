@@ -39,6 +39,12 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
 int backtransform2_launch(const Plan* pl, const double* K, int ldk, const BandBuffers& bb, const double* x,
                           const double* beta0, double* out, size_t out_stride, int T, cudaStream_t st);
 size_t chase_workspace(const Plan* pl, int T);
+size_t chase_prog_ints(const Plan* pl, int T);
+// per-device set-up (function attributes, occupancy queries), called by chd_plan_create on the plan's device
+int chase_device_init(Plan* pl);
+int band_device_init(Plan* pl);
+int tridiag_device_init(Plan* pl);
+int act_device_init(Plan* pl);
 int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e, int T, cudaStream_t st);
 int band_solve_launch(const Plan* pl, const double* bandS, double* Lg, const double* gu, double* Bq, int ldb, int nz,
                       double* x, double* noise, double* z_low, double* z_high, size_t out_stride, int T,

@@ -976,14 +976,6 @@ int tridiag_launch(const Plan* pl, double* K, int ldk, const double* ga, int T, 
   static const bool dbg_on = getenv("CHD_TD_TIMING") != nullptr;
   if (dbg_on && !dbg) CHD_CUDA(cudaMalloc(&dbg, 8 * sizeof(unsigned long long)));
   a.timing = dbg_on ? dbg : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    void* fns[4] = {(void*)tridiag_kernel<256, false>, (void*)tridiag_kernel<512, false>,
-                    (void*)tridiag_kernel<256, true>, (void*)tridiag_kernel<512, true>};
-    for (void* f : fns)
-      CHD_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
-    attr_set = true;
-  }
   void* kfn = pl->bulk ? (pl->threads == 256 ? (void*)tridiag_kernel<256, true> : (void*)tridiag_kernel<512, true>)
                        : (pl->threads == 256 ? (void*)tridiag_kernel<256, false> : (void*)tridiag_kernel<512, false>);
   if (smem > pl->smem_optin) {
@@ -1030,14 +1022,16 @@ int backtransform_launch(const Plan* pl, const double* K, int ldk, const Tridiag
   a.K = K; a.strideK = (size_t)pl->n * ldk; a.ldk = ldk; a.v0 = tb.v0; a.tau = tb.tau; a.pgram = tb.pgram;
   a.x = x; a.beta0 = beta0; a.out = out; a.out_stride = out_stride; a.n = pl->n; a.nb = pl->nb;
   const size_t smem = ((size_t)pl->n + 2 * TD_MAXNB + TD_MAXNB * TD_MAXNB + 8) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CHD_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->smem_optin));
-    attr_set = true;
-  }
   backtransform_kernel<<<T, 512, smem, st>>>(a);
   CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+int tridiag_device_init(Plan* pl) {
+  void* fns[5] = {(void*)tridiag_kernel<256, false>, (void*)tridiag_kernel<512, false>,
+                  (void*)tridiag_kernel<256, true>, (void*)tridiag_kernel<512, true>, (void*)backtransform_kernel};
+  for (void* f : fns)
+    CHD_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
   return CHD_OK;
 }
 

@@ -56,11 +56,11 @@ def activations(spec, X, yb, ga, active_modes, has_clusters, exps=None):
     energy = -np.dot(ga, yb)
     empty = np.all(active_modes == 0, axis=1)
     C = active_modes.shape[0]
-    if spec.name == "linear" and not has_clusters:             # HELP:59-79
+    if spec.name == "linear" and spec.fn is None and not has_clusters:   # HELP:59-79 (isinstance LinearMode)
         cols = X[:, np.argmax(active_modes, axis=1)]            # (n, C)
         vecs = cols * yb[:, None]
         act = spec.scale * np.sum(vecs, axis=0) ** 2 / energy
-    elif spec.name == "quadratic" and not has_clusters:        # HELP:81-111
+    elif spec.name == "quadratic" and spec.fn is None and not has_clusters:   # HELP:81-111
         w = np.sum(active_modes, axis=0)
         K_all = 2 * (spec.alpha + linear_core(X, X, w))
         cols = X[:, np.argmax(active_modes, axis=1)]
@@ -279,6 +279,8 @@ def fit(X, names, kernels=None, normalize_data=True, clusters=None, adjacency=No
     for t in range(T):
         if kernel_chooser[0] == "min_noise":
             chosen[t], sel[t] = min_noise_kernel_chooser(perf["noises"][t], perf["Z_lows"][t])
+        elif kernel_chooser[0] == "force":       # test hook: a user KernelChooser that always picks one index
+            chosen[t] = sel[t] = int(kernel_chooser[1])
         else:
             chosen[t], sel[t] = threshold_kernel_chooser(perf["noises"][t], kernel_chooser[1])
     ar = np.arange(T)

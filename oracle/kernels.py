@@ -18,12 +18,13 @@ class KernelSpec:
     """Plain description of one mode kernel as the reference configures it in
     `setup()` (KERN:108-123, 187-209, 293-317)."""
 
-    def __init__(self, name, scale, alpha=None, quad_scale=None, l=None):
-        self.name = name          # "linear" | "quadratic" | "gaussian"
+    def __init__(self, name, scale, alpha=None, quad_scale=None, l=None, fn=None):
+        self.name = name          # "linear" | "quadratic" | "gaussian" | a user ModeKernel's name
         self.scale = float(scale)
         self.alpha = alpha        # quadratic shift (quadratic & gaussian)
         self.quad_scale = quad_scale  # scale of the gaussian's internal quadratic part
         self.l = l
+        self.fn = fn              # user ModeKernel: kernel(X, Y, which_dim) (KERN:7-68)
 
     def __repr__(self):
         return self.name
@@ -37,7 +38,9 @@ def make_specs(kernels):
     scales = {name: scale for (name, scale, _l) in kernels}
     specs = []
     for (name, scale, l) in kernels:
-        if name == "linear":
+        if callable(l):           # user ModeKernel (name, scale, kernel function)
+            specs.append(KernelSpec(name, scale, fn=l))
+        elif name == "linear":
             specs.append(KernelSpec("linear", scale))
         elif name == "quadratic":
             if "linear" not in scales:
@@ -84,6 +87,8 @@ def gaussian_product(X, Y, w, l, exps=None):
 def gram(spec, X, Y, w, exps=None):
     """kernel(X, Y, which_dim)  (ModeKernel.__call__ KERN:58-59).  `exps`: optional cache (X is Y)."""
     w = np.asarray(w, dtype=np.float64)
+    if spec.fn is not None:
+        return np.asarray(spec.fn(X, Y, w), dtype=np.float64)
     L = linear_core(X, Y, w)
     if spec.name == "linear":
         return 1 + spec.scale * L
@@ -107,6 +112,11 @@ def individual_influence(spec, X, Y, w, w_only, exps=None):
     211-228, 319-334."""
     w = np.asarray(w, dtype=np.float64)
     w_only = np.asarray(w_only, dtype=np.float64)
+    if spec.fn is not None:
+        own = getattr(spec.fn, "individual_influence", None)     # a user subclass may override the hook
+        if own is not None:
+            return np.asarray(own(X, Y, w, w_only), dtype=np.float64)
+        return gram(spec, X, Y, w) - gram(spec, X, Y, w * (1 - w_only))   # ModeKernel default, KERN:39-56
     if spec.name == "linear":
         return gram(spec, X, Y, w_only) - 1                      # KERN:104-106
     if spec.name == "quadratic":

@@ -27,6 +27,31 @@ def _fit_cuda(X, names, kernels=None, **kw):
     return gd
 
 
+# Bookkeeping of the BFGS `success`-flag escape hatch: how often it fired, over how many
+# compared chains.  conftest.py writes it to gpurun_out/parity_notes.json at the end of a GPU session; bench.py
+# quotes the committed copy (profiles/) as `parity_notes`.
+FLIP_STATS = {"fits_compared": 0, "chains_compared": 0, "chain_steps_compared": 0, "flag_flips": 0,
+              "chain_steps_excluded": 0, "flips": []}
+
+
+def flip_report():
+    f = FLIP_STATS
+    return (f"BFGS success-flag flips so far: {f['flag_flips']} in {f['chains_compared']} chains / "
+            f"{f['chain_steps_compared']} chain steps ({f['chain_steps_excluded']} steps excluded after a flip)")
+
+
+def _force_chooser(k):
+    """A user KernelChooser (DEC:8-31 interface) that always picks kernel k."""
+    import computationalhypergraphdiscovery_b200 as CHD
+
+    class Force(CHD.decision.KernelChooser):
+        def __call__(self, perfs):
+            ybs, noises, zl, zh, gammas, keys = perfs
+            return k, ybs[k], noises[k], zl[k], zh[k], gammas[k], keys[k]
+
+    return Force()
+
+
 def _flag_flips(gd, res):
     """{target name: first chain step} where gamma differs from the oracle's because the BFGS `success` flag of
     interpolatory.py:133-134 came out the other way.  Near convergence that flag is decided by rounding noise of
@@ -44,6 +69,17 @@ def _flag_flips(gd, res):
                 alt = ch["alt_gammas"][i, s0]
                 assert abs(mine["gammas"][i, s0] - alt) <= 1e-5 * abs(alt), (name, s0, mine["gammas"][i, s0], alt)
                 flips[name] = s0
+                FLIP_STATS["flag_flips"] += 1
+                FLIP_STATS["chain_steps_excluded"] += int(ch["gammas"].shape[1] - s0)
+                FLIP_STATS["flips"].append({"target": str(name), "kernel": int(k), "step": s0,
+                                            "n": int(gd.X.shape[0]), "N": int(gd.X.shape[1]),
+                                            "gamma_oracle": float(ch["gammas"][i, s0]),
+                                            "gamma_cuda": float(mine["gammas"][i, s0])})
+        FLIP_STATS["chains_compared"] += len(ch["targets"])
+        FLIP_STATS["chain_steps_compared"] += int(ch["gammas"].size)
+    FLIP_STATS["fits_compared"] += 1
+    if flips:
+        print(f"\n[parity] {len(flips)} BFGS success-flag flip(s) in this fit: {flips}; {flip_report()}")
     return flips
 
 
@@ -111,6 +147,42 @@ def test_synthetic_fit_matches_oracle():
     _compare_with_oracle(gd, res, names, {})
 
 
+def test_multi_batch_gaussian_chain_matches_oracle():
+    """a kernel group larger than one launch batch (forced here: 3 targets per batch) reuses ONE Gaussian
+    product-map buffer across its batches and writes the chain slices batch by batch."""
+    import computationalhypergraphdiscovery_b200 as CHD
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    X, names = make_data(160, 8, seed=21)
+    gd = CHD.GraphDiscovery(X, names, verbose=False)
+    gd._force_batch_size = 3
+    gd.fit(kernel_chooser=_force_chooser(2))
+    res = ochd.fit(X, names, kernel_chooser=("force", 2))
+    assert gd.last_fit["chains"][2]["noises"].shape == (8, 7)
+    _compare_with_oracle(gd, res, names, {})
+
+
+def test_group_with_empty_initial_masks_runs_one_step():
+    """ADVICE r1 / MAIN:619-660: with possible_edges a target can start with no candidate ancestor at all; the
+    reference still runs ONE prune step (the `all masks empty` check comes after the step).  The regression of that
+    step is on the constant Gram matrix (rank-deficient: values are not comparable), so only the
+    shape of the chain and the absence of garbage are checked."""
+    import networkx as nx
+    import computationalhypergraphdiscovery_b200 as CHD
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    X, names = make_data(120, 5, seed=22)
+    pe = nx.DiGraph()
+    pe.add_nodes_from(names)
+    pe.add_edges_from((a, b) for a in names for b in names[1:] if a != b)      # nothing may point to names[0]
+    gd = CHD.GraphDiscovery(X, names, possible_edges=pe, verbose=False)
+    gd.fit(targets=[names[0]], kernel_chooser=_force_chooser(1))
+    ch = gd.last_fit["chains"][1]
+    assert ch["noises"].shape == (1, 2) and ch["activations"].shape == (1, 1, 5)
+    assert (ch["activations"] == 2.0).all()
+    assert (ch["active"] == 0).all()
+    assert np.isfinite(ch["noises"]).all() or np.isnan(ch["noises"][0, 1])
+    assert gd.G.in_degree(names[0]) == 0
+
+
 def test_sachs_shaped_linear_quadratic():
     """Config 1 shape: n=500, N=11, LinearMode + QuadraticMode."""
     import computationalhypergraphdiscovery_b200 as CHD
@@ -140,7 +212,7 @@ def test_predictions_example1_golden(golden_dir):
     assert f"{gd.G.nodes['$x_2$']['noise']:.3g}" == "0.000991"
 
 
-@pytest.mark.parametrize("ex", [0, 2])
+@pytest.mark.parametrize("ex", [0, 1, 2, 3])
 def test_algebraic_golden(golden_dir, ex):
     gold = json.load(open(os.path.join(golden_dir, "algebraic.json")))["examples"][ex]
     X, names = algebraic_examples()[ex]
@@ -271,11 +343,78 @@ def test_custom_mode_kernel_extension_hook():
     gd.fit()
     assert sorted(gd.G.edges) == sorted(ref.G.edges)
     np.testing.assert_allclose(gd.last_fit["stage1"][1], ref.last_fit["stage1"][1], rtol=1e-9)
-    for k in ref.last_fit["chains"]:
-        np.testing.assert_allclose(gd.last_fit["chains"][k]["noises"], ref.last_fit["chains"][k]["noises"], rtol=1e-7)
-        m = ref.last_fit["chains"][k]["activations"] != 2.0
-        np.testing.assert_allclose(gd.last_fit["chains"][k]["activations"][m],
-                                   ref.last_fit["chains"][k]["activations"][m], rtol=1e-7)
     for nm in names:
         if "type" in gd.G.nodes[nm]:
             assert gd.G.nodes[nm]["type"] == "myquad"
+
+
+def _user_kernels():
+    import computationalhypergraphdiscovery_b200 as CHD
+
+    class Cubic(CHD.Modes.ModeKernel):
+        """K = 1 + s (L + L^3 / 4): not one of the built-in modes, default individual_influence (KERN:39-56)."""
+
+        def __init__(self):
+            super().__init__()
+            self.name = "cubic"
+            self._is_interpolatory = False
+            self._memory_efficient_required = False
+
+        def setup(self, X, scales):
+            assert self.scale == scales[self.name]
+
+        def kernel(self, X, Y, which_dim):
+            L = (X * which_dim[None, :]) @ Y.T
+            return 1 + self.scale * (L + L ** 3 / 4)
+
+    class Laplace(CHD.Modes.ModeKernel):
+        """K = prod_d (1 + w_d exp(-|x_d - y_d|)) with its own individual_influence (the hook of KERN:39-56)."""
+
+        def __init__(self):
+            super().__init__()
+            self.name = "laplace"
+            self._is_interpolatory = True
+            self._memory_efficient_required = True
+
+        def setup(self, X, scales):
+            assert self.scale == scales[self.name]
+
+        def _prod(self, X, Y, w):
+            P = np.ones((X.shape[0], Y.shape[0]))
+            for d in np.nonzero(w)[0]:
+                P *= 1 + w[d] * np.exp(-np.abs(X[:, d][:, None] - Y[:, d][None, :]))
+            return P
+
+        def kernel(self, X, Y, which_dim):
+            return self.scale * self._prod(X, Y, which_dim)
+
+        def individual_influence(self, X, Y, which_dim, which_dim_only):
+            rest = which_dim * (1 - which_dim_only)
+            return self.scale * (self._prod(X, Y, which_dim_only) - 1) * self._prod(X, Y, rest)
+
+    return Cubic, Laplace
+
+
+@pytest.mark.parametrize("clustered", [False, True])
+def test_custom_mode_kernels_match_oracle(clustered):
+    """Row f4: user ModeKernels (host Gram -> chd_regress, activations through individual_influence) against
+    `oracle.chd.fit` running the same Python kernels through the reference's generic path (HELP:113-132)."""
+    import computationalhypergraphdiscovery_b200 as CHD
+    from computationalhypergraphdiscovery_b200.synthetic import make_data
+    Cubic, Laplace = _user_kernels()
+    X, names = make_data(160, 7, seed=12)
+    clusters = [names[0:2], names[2:3], names[3:5], names[5:6], names[6:7]] if clustered else None
+    cub, lap = 0.5 * Cubic(), 1.5 * Laplace()
+    gd = CHD.GraphDiscovery(X, names, kernels=[cub, lap], clusters=clusters, verbose=False)
+    # without clusters every node prefers the Laplace kernel: force the cubic one there so both get chains
+    gd.fit(kernel_chooser=None if clustered else _force_chooser(0))
+    ocub, olap = 0.5 * Cubic(), 1.5 * Laplace()
+
+    def lap_fn(A, B, w):
+        return olap.kernel(A, B, w)
+
+    lap_fn.individual_influence = olap.individual_influence
+    res = ochd.fit(X, names, kernels=[("cubic", 0.5, ocub.kernel), ("laplace", 1.5, lap_fn)], clusters=clusters,
+                   kernel_chooser=("min_noise",) if clustered else ("force", 0))
+    assert set(res["chains"]) == set(gd.last_fit["chains"]) and len(res["chains"]) >= 1
+    _compare_with_oracle(gd, res, names, {})
