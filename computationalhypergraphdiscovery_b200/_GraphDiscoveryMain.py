@@ -182,9 +182,7 @@ class GraphDiscovery:
             mode_chooser = MaxIncrementModeChooser()
         else:
             mode_chooser.is_a_mode_chooser()
-        if key is None:
-            key = chd_random.PRNGKey(0)
-        key = np.asarray(key, dtype=np.uint32)
+        key = chd_random.as_key(key)
         if targets is None:
             targets = self.names
         all_targets = list(targets)
@@ -595,38 +593,21 @@ class GraphDiscovery:
             index += 1
 
     def plot_graph(self, type_label=True, **kwargs):
-        """Plots the hypergraph (MAIN:819-932); needs matplotlib."""
+        """Draws G (MAIN:819-932); out of the hot path: a plain networkx drawing (clusters through
+        util.partition_layout), matplotlib required."""
         if not have_matplotlib():
             raise RuntimeError("plot_graph needs matplotlib, which is not installed")
-        import matplotlib.pyplot as plt
-        node_size = kwargs.get("node_size", 400)
-        cluster_size = kwargs.get("cluster_size", 10000)
-        font_size = kwargs.get("font_size", 8)
-        with_labels = kwargs.get("with_labels", True)
-        alpha = kwargs.get("alpha", 0.6)
-        connection_style = kwargs.get("connection_style", "arc3,rad=0")
-        between_cluster_edge_style = kwargs.get("between_cluster_edge_style", "dashed")
-        cluster_edge_color = kwargs.get("cluster_edge_color", "red")
-        if not self.has_clusters:
-            plt.figure(figsize=(10, 4))
-            pos = nx.kamada_kawai_layout(self.G, self.G.nodes())
-            nx.draw_networkx(self.G, with_labels=with_labels, pos=pos, node_size=node_size, font_size=font_size,
-                             alpha=alpha)
-            if type_label:
-                nx.draw_networkx_edge_labels(self.G, pos, edge_labels=nx.get_edge_attributes(self.G, "type"))
-            return
-        cluster_partition = {item: i for i, sublist in enumerate(self.modes.clusters) for item in sublist}
-        pos, hypergraph = partition_layout(self.G, cluster_partition)
-        node_sizes = [node_size if (node in self.G) else cluster_size for node in hypergraph.nodes()]
-        nx.draw_networkx_nodes(hypergraph, pos=pos, nodelist=self.G.nodes(), node_size=node_size, alpha=alpha)
-        nx.draw_networkx_edges(hypergraph, pos, node_size=node_sizes, alpha=alpha, style=between_cluster_edge_style,
-                               edgelist=[e for e in hypergraph.edges if not hypergraph.edges[e]["intra_cluster"]],
-                               connectionstyle=connection_style)
-        nx.draw_networkx_edges(hypergraph, pos, node_size=node_size, alpha=0.6, connectionstyle=connection_style,
-                               edgelist=[e for e in hypergraph.edges if hypergraph.edges[e]["intra_cluster"]])
-        nx.draw_networkx_nodes(hypergraph, pos, nodelist=set(cluster_partition.values()), node_color="None",
-                               node_size=cluster_size, edgecolors=cluster_edge_color)
-        nx.draw_networkx_labels(hypergraph, pos, labels={node: node for node in self.G.nodes()}, font_size=font_size)
+        if self.has_clusters:
+            partition = {item: i for i, sublist in enumerate(self.modes.clusters) for item in sublist}
+            pos, _hyper = partition_layout(self.G, partition)
+            pos = {k: v for k, v in pos.items() if k in self.G}
+        else:
+            pos = nx.kamada_kawai_layout(self.G)
+        nx.draw_networkx(self.G, pos=pos, with_labels=kwargs.get("with_labels", True),
+                         node_size=kwargs.get("node_size", 400), font_size=kwargs.get("font_size", 8),
+                         alpha=kwargs.get("alpha", 0.6))
+        if type_label:
+            nx.draw_networkx_edge_labels(self.G, pos, edge_labels=nx.get_edge_attributes(self.G, "type"))
 
     # ------------------------------------------------------------------ predict
     def predict(self, names, X_pred):

@@ -54,8 +54,6 @@ _SIGNATURES = {
     "chd_tridiag": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "chd_dmma_peak": (_i, [_i, ctypes.POINTER(_d)]),
     "chd_fp64_probe": (_i, [_i, _i, ctypes.POINTER(_d)]),
-    "chd_gamma_band": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                            _vp, _sz, _vp]),
     "chd_band_workspace_bytes": (_sz, [_vp, _i]),
     "chd_band_reduce": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "chd_band_backtransform": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
@@ -204,23 +202,6 @@ class Plan:
                                   _ptr(out["z_low"]), _ptr(out["z_high"]), _ptr(out["gamma"]), _ptr(out["keys"]),
                                   _ptr(out["lambda_min"]), _ptr(out["status"]), _ptr(ws), ws.numel(), _stream()),
                "chd_regress")
-        return out
-
-    def gamma_band(self, B, band, gt, Bq, gamma_min, mode=1, base=1e-9):
-        """Narrow-band building block: band (T, B+1, n), gt (T, B), Bq (T, n, nz) overwritten."""
-        T = band.shape[0]
-        dev, f64 = self.device, torch.float64
-        out = dict(x=torch.empty((T, self.n), dtype=f64, device=dev), noise=torch.empty(T, dtype=f64, device=dev),
-                   z_low=torch.empty(T, dtype=f64, device=dev), z_high=torch.empty(T, dtype=f64, device=dev),
-                   gamma=torch.empty(T, dtype=f64, device=dev), lambda_min=torch.empty(T, dtype=f64, device=dev),
-                   status=torch.zeros(T, dtype=torch.int32, device=dev), gamma_min=gamma_min)
-        ws = self.workspace(T)
-        nz = Bq.shape[2] if Bq is not None else 0
-        _check(load().chd_gamma_band(self._h, int(B), _ptr(band), _ptr(gt), _ptr(Bq), nz, nz, T, _ptr(self.grid),
-                                     int(mode), float(base), _ptr(gamma_min), _ptr(out["x"]), _ptr(out["noise"]),
-                                     _ptr(out["z_low"]), _ptr(out["z_high"]), _ptr(out["gamma"]),
-                                     _ptr(out["lambda_min"]), _ptr(out["status"]), _ptr(ws), ws.numel(), _stream()),
-               "chd_gamma_band")
         return out
 
     # ---- two-stage building blocks

@@ -420,8 +420,11 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
 }
 
 int act_device_init(Plan* pl) {
+  // the kernel also has static shared memory: the opt-in limit covers static + dynamic
+  cudaFuncAttributes fa;
+  CHD_CUDA(cudaFuncGetAttributes(&fa, gauss_pairs_kernel));
   CHD_CUDA(cudaFuncSetAttribute(gauss_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)pl->smem_optin));
+                                (int)(pl->smem_optin - fa.sharedSizeBytes)));
   return CHD_OK;
 }
 

@@ -385,25 +385,6 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
   return CHD_OK;
 }
 
-extern "C" int chd_gamma_band(const chd_plan* plan, int B, const double* band, const double* gt, double* Bq, int ldb,
-                              int nz, int T, const double* gamma_grid, int gamma_min_mode, double gamma_min_base,
-                              double* gamma_min, double* x, double* noise, double* z_low, double* z_high,
-                              double* gamma, double* lambda_min, int32_t* status, void* workspace,
-                              size_t workspace_bytes, void* stream) {
-  const Plan* pl = (const Plan*)plan;
-  if (!pl || !band || !gt || !gamma_grid || !gamma_min || !x || !noise || !z_low || !z_high || !gamma || !status ||
-      T <= 0 || (B != 1 && B != 2 && B != 4) || pl->n < 2 * B)
-    return CHD_EINVAL;
-  Carver cv(workspace, workspace_bytes);
-  double* loss = cv.take<double>((size_t)T * CHD_GRID_POINTS);
-  double* Dg = cv.take<double>((size_t)T * pl->n);
-  double* Ug = cv.take<double>((size_t)T * pl->n * B);
-  if (!cv.ok) return CHD_ENOSPC;
-  return gamma_band_launch(pl, B, band, gt, gamma_grid, loss, Bq, ldb, Bq ? nz : 0, gamma_min_mode, gamma_min_base,
-                           gamma_min, lambda_min != nullptr, lambda_min, Dg, Ug, x, noise, z_low, z_high, gamma, 1,
-                           status, T, (cudaStream_t)stream);
-}
-
 // ---- two-stage building blocks (inspection / test entry points)
 struct BandWs {
   BandBuffers bb;

@@ -21,11 +21,6 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
                  double* gamma_min, int want_lambda_min, double* lambda_min, double* eta, double* uu, double* x,
                  double* noise, double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status,
                  int T, cudaStream_t st, double* gu_out = nullptr);
-int gamma_band_launch(const Plan* pl, int B, const double* band, const double* gt, const double* grid, double* loss,
-                      double* Bq, int ldb, int nz, int gamma_min_mode, double gamma_min_base, double* gamma_min,
-                      int want_lambda_min, double* lambda_min, double* Dg, double* Ug, double* x, double* noise,
-                      double* z_low, double* z_high, double* gamma, size_t out_stride, int32_t* status, int T,
-                      cudaStream_t st);
 // ---- two-stage reduction (band.cu, chase.cu, bandsolve.cu)
 struct BandBuffers {
   double *V, *Y, *W, *Tf, *Mpart, *Zpart, *Mred, *Zred, *v0, *tau0, *bandS, *bandW;

@@ -143,14 +143,6 @@ int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, const double* X
  * B (T x n x ldb, may be NULL, nb_cols columns) is overwritten with Q^T B. Reflectors stay in K. */
 int chd_tridiag(const chd_plan* plan, double* K, int ldk, const double* ga, int T, double* B, int ldb, int nb_cols,
                 double* d, double* e, double* beta0, void* workspace, size_t workspace_bytes, void* stream);
-/* Narrow-band building block: gamma search, solve, noise and Z-test on a symmetric band
- * form T_b = Q^T K Q of half-width B (1, 2 or 4): band (T x (B+1) x n, band[t][k] = T_b[k][k-t]), gt (T x B, the
- * non-zero head of Q^T ga), Bq = Q^T S (T x n x ldb, nz columns, overwritten).  Outputs as chd_regress, plus
- * x (T x n) = (T_b + gamma_used I)^-1 [gt; 0] (the caller maps it back with Q). */
-int chd_gamma_band(const chd_plan* plan, int B, const double* band, const double* gt, double* Bq, int ldb, int nz,
-                   int T, const double* gamma_grid, int gamma_min_mode, double gamma_min_base, double* gamma_min,
-                   double* x, double* noise, double* z_low, double* z_high, double* gamma, double* lambda_min,
-                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 /* Two-stage reduction building blocks (inspection / test entry points -- chd_regress and
  * chd_prune_chain run the same kernels when the plan is in two-stage mode).  Replace, together, the eigh of
  * interpolatory.py:48.  CHD_BAND = 32 is the half-width of the band form; band arrays are T x n x CHD_BAND_LD with

@@ -203,42 +203,3 @@ def test_activations_match_oracle(clusters):
             assert alive_d[t, j].item() == 0
 
 
-@pytest.mark.parametrize("B", [1, 2, 4])
-def test_gamma_band_matches_oracle(B):
-    """Narrow-band downstream (gamma search / solve / Z-test on a band form of half-width B) fed with the band
-    form produced by the NumPy model (tests/band_model.py), against the oracle's eigendecomposition path."""
-    import band_model as bmod
-    nat = _native()
-    n, N = 150, 6
-    X, _ = _data(n, N, 12)
-    plan = nat.Plan(n, N, N)
-    dev = plan.device
-    w = np.ones(N)
-    w[0] = 0
-    ga = X[:, 0].copy()
-    key = jaxprng.PRNGKey(5)
-    ks = jaxprng.split(key)
-    S = jaxprng.normal(ks[1], (n, 100))
-    bands, gts, Bqs, refls = [], [], [], []
-    for spec in SPECS:
-        K = okern.gram(spec, X, X, w)
-        band, gt, refl, resid = bmod.band_reduce(K, ga, B)
-        bands.append(band); gts.append(gt); Bqs.append(bmod.apply_QT(refl, S)); refls.append(refl)
-    T = len(SPECS)
-    band_d = torch.from_numpy(np.ascontiguousarray(np.stack(bands))).to(dev)
-    gt_d = torch.from_numpy(np.ascontiguousarray(np.stack(gts))).to(dev)
-    Bq_d = torch.from_numpy(np.ascontiguousarray(np.stack(Bqs))).to(dev)
-    gmin = torch.full((T,), 1e-9, dtype=torch.float64, device=dev)
-    r = plan.gamma_band(B, band_d, gt_d, Bq_d, gmin, mode=1, base=1e-9)
-    torch.cuda.synchronize()
-    for t, spec in enumerate(SPECS):
-        K = okern.gram(spec, X, X, w)
-        info = {}
-        yb, noise, zl, zh, gamma, _k = oreg.perform_regression_and_find_gamma(K, ga, 1e-9, key, info)
-        assert abs(r["gamma"][t].item() - gamma) <= 1e-6 * abs(gamma), (spec, r["gamma"][t].item(), gamma)
-        assert abs(r["noise"][t].item() - noise) <= 1e-8 * abs(noise)
-        assert abs(r["z_low"][t].item() - zl) <= 1e-8 * abs(zl)
-        assert abs(r["z_high"][t].item() - zh) <= 1e-8 * abs(zh)
-        assert abs(r["lambda_min"][t].item() - info["eigenvalues"][0]) < 1e-11 * abs(info["eigenvalues"][-1])
-        ybd = -bmod.apply_Q(refls[t], r["x"][t].cpu().numpy())
-        assert np.linalg.norm(ybd - yb) <= 1e-7 * np.linalg.norm(yb)
