@@ -193,10 +193,14 @@ class GraphDiscovery:
         targets = parallel.shard_targets(all_targets, rank, world)
         pos = {name: i for i, name in enumerate(all_targets)}
         subkeys = subkeys_all[[pos[t] for t in targets]] if targets else subkeys_all[:0]
+        counts = [len(parallel.shard_targets(all_targets, r, world)) for r in range(world)]
+        n_s, L = self.X.shape[0], max(len(self.modes.clusters) - 2, 0)
         if world > 1 and not targets:
             # more ranks than targets: nothing to compute here, but take part in the two collectives
-            parallel.all_gather_list([-1] * len(self.kernels))
-            parallel.merge_node_results(self.G, parallel.all_gather_results({}))
+            parallel.all_gather_ints([-1] * len(self.kernels))
+            rec = parallel.all_gather_records(np.zeros((0, parallel.record_words(n_s, len(self.names), L))), counts)
+            self.last_fit = dict(targets=[], gathered=parallel.unpack_node_results(
+                self.G, all_targets, self.names, self.kernels, n_s, L, rec))
             return
         gas_idx, w0 = self._prepare_modes_for_ancestor_finding(targets)
 
@@ -211,7 +215,7 @@ class GraphDiscovery:
         group_rows = [int(rows0[chosen_kernels == i].max()) if np.any(chosen_kernels == i) else -1
                       for i in range(len(self.kernels))]
         if world > 1:
-            group_rows = [max(v) for v in zip(*parallel.all_gather_list(group_rows))]
+            group_rows = [int(v) for v in parallel.all_gather_ints(group_rows).max(axis=0)]
         for i, kernel in enumerate(self.kernels):
             mask_kernel = chosen_kernels == i
             if not np.any(mask_kernel):
@@ -232,14 +236,21 @@ class GraphDiscovery:
             self.last_fit["chains"][i] = dict(
                 targets=[t for t, m in zip(targets, mask_kernel) if m], active=active_modess_kernel,
                 noises=noisess_kernel, raw_noises=raw_noises, Z_lows=Z_lows_kernel, Z_highs=Z_highs_kernel,
-                activations=activationss_kernel, gammas=gammas_kernel, chosen_modes=chosen_modes)
+                activations=activationss_kernel, gammas=gammas_kernel, chosen_modes=chosen_modes,
+                pruned=self._chain_pruned)
             self.process_results(targets, i, mask_kernel, chosen_modes, active_modess_kernel, noisess_kernel,
                                  Z_lows_kernel, Z_highs_kernel, activationss_kernel, kernel_performance,
                                  gammas_kernel, ybs_kernel)
         self.process_results(targets, -1, chosen_kernels == -1, *([None] * 6), kernel_performance, None, None)
-        if world > 1:   # one all-gather of the per-node results
-            merged = parallel.all_gather_results(parallel.export_node_results(self.G, targets))
-            parallel.merge_node_results(self.G, merged)
+        if world > 1:
+            # ONE all-gather of the packed per-node results; every rank then rebuilds the nodes and
+            # edges of ALL targets from the records, in target order, so G does not depend on the number of GPUs
+            rec = parallel.pack_node_results(self.G, targets, self.names, n_s, L, self.last_fit["chains"])
+            rec = parallel.all_gather_records(rec, counts)
+            for name in targets:                     # drop the locally written copies: rebuilt below, in order
+                self.G.remove_edges_from(list(self.G.in_edges(name)))
+            self.last_fit["gathered"] = parallel.unpack_node_results(
+                self.G, all_targets, self.names, self.kernels, n_s, L, rec)
 
     @staticmethod
     def _anomaly_clamp(noises, zl, zh):
@@ -529,6 +540,7 @@ class GraphDiscovery:
         for st in range(S):
             alive_h[np.arange(Tk), pruned[:, st]] = 0
             active[:, st + 1] = w0 * alive_h[:, cluster_of]
+        self._chain_pruned = pruned
         return active, noises, zl, zh, activations, gm, yb_chain
 
     def _nonempty(self, w0, alive):
