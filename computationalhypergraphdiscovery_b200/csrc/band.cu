@@ -17,8 +17,17 @@
 //   reduce_kernel    fixed-order sum of the per-CTA partials (deterministic, no atomics)
 //   wform_kernel     W = (Y - 1/2 V T^T (V^T Y)) T,  B -= V T^T (V^T B)
 //   syr2k_kernel     A22 -= V W^T + W V^T on the lower tiles (DMMA, K = 2 NB)
-// Everything is GEMM-shaped: 4/3 n^3 flop on the tensor cores, the trailing matrix is read
-// 2x and written 1x per panel (n/NB panels) instead of once per column.
+// Everything is GEMM-shaped: 4/3 n^3 flop on the tensor cores.
+//
+// DEFERRED trailing update (default, CHD_KD=2): panels are processed in groups of KD = 2 (slot 0 = H_{-1}, slots
+// 1.. = QR panels; groups (0,1), (2,3), ...).  Inside a group the trailing matrix stays stale: the second panel's
+// block column is brought up to date by panel_update_kernel, its Y = A22 V comes from the stale matrix plus the
+// corrections  Y -= V_a (W_a^T V) + W_a (V_a^T V)  (the two 32 x 32 Gram blocks are partials of the symm epilogue,
+// M = V^T Y follows from them without a second reduction), and ONE update with K = 4 NB = 128
+//   A22 -= [V_a V_b | W_a W_b] [W_a W_b | V_a V_b]^T
+// closes the group: the trailing matrix is read 3x and written 1x per TWO panels instead of 4x / 2x, and the update
+// runs at 16 flop per byte of trailing-matrix traffic instead of 8 (NumPy model + proof of equivalence:
+// tests/twostage_model.py::stage1_deferred).
 #include <cooperative_groups.h>
 
 #include <stdlib.h>
@@ -30,6 +39,8 @@ namespace cg = cooperative_groups;
 namespace chd {
 
 constexpr int NB = CHD_BAND;
+constexpr int KD = 2;               // panels per deferred-update group
+constexpr int LDV = NB * KD;        // row stride of the V / W operand arrays: [panel q = 0 | panel q = 1]
 constexpr int QR_THREADS = 256;
 constexpr int QR_S = NB + 1;        // shared-memory row stride of the panel slice
 constexpr int QR_MAXCS = 16;
@@ -47,7 +58,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ------------------------------------------------------------------ H_{-1}
 struct Refl0Args {
   const double* ga;   // T x n
-  double* V;          // T x n x NB   (column 0 = v0, the rest 0)
+  double* V;          // T x n x LDV, columns 0..NB-1 (column 0 = v0, the rest 0)
   double* v0;         // T x n
   double* Tf;         // T x tf_stride (slot 0 = diag(tau0, 0, ...))
   size_t tf_stride;
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(256) refl0_kernel(Refl0Args a) {
     tau = (beta - alpha) / beta;
     scale = 1.0 / (alpha - beta);
   }
-  double* V = a.V + (size_t)t * n * NB;
+  double* V = a.V + (size_t)t * n * LDV;
   double* v0 = a.v0 + (size_t)t * n;
   for (int i = tid; i < n; i += blockDim.x) {
     const double v = (i == 0) ? 1.0 : ga[i] * scale;
@@ -80,7 +91,7 @@ __global__ void __launch_bounds__(256) refl0_kernel(Refl0Args a) {
   }
   for (int e = tid; e < n * NB; e += blockDim.x) {
     const int i = e / NB, c = e % NB;
-    V[e] = (c == 0) ? ((i == 0) ? 1.0 : ga[i] * scale) : 0.0;
+    V[(size_t)i * LDV + c] = (c == 0) ? ((i == 0) ? 1.0 : ga[i] * scale) : 0.0;
   }
   double* Tf = a.Tf + (size_t)t * a.tf_stride;
   for (int e = tid; e < NB * NB; e += blockDim.x) Tf[e] = (e == 0) ? tau : 0.0;
@@ -90,7 +101,7 @@ __global__ void __launch_bounds__(256) refl0_kernel(Refl0Args a) {
 // ------------------------------------------------------------------ panel QR (cluster kernel)
 struct QrArgs {
   double* A; size_t strideA; int ldk;
-  double* V;        // T x n x NB
+  double* V;        // T x n x LDV, already offset to this panel's column block (q NB)
   double* Tf;       // T x tf_stride, already offset to this panel's slot
   size_t tf_stride;
   int n, r0, c0;
@@ -271,12 +282,12 @@ __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(QrArgs a) {
     for (int e = tid; e < NB * NB; e += QR_THREADS) Tf[e] = Ts[(e / NB) * QR_S + (e % NB)];
   }
   // ---- outputs: the factored block in place (R over V), V as a dense operand
-  double* V = a.V + (size_t)t * n * NB + (size_t)(r0 + pr0) * NB;
+  double* V = a.V + (size_t)t * n * LDV + (size_t)(r0 + pr0) * LDV;
   for (int e = tid; e < nrows * NB; e += QR_THREADS) {
     const int lr = e / NB, c = e % NB, pr = pr0 + lr;
     const double x = rowp(lr)[c];
     if (lr < RS) Ag[(size_t)lr * ldk + c] = x;
-    V[e] = (c >= nref || pr < c) ? 0.0 : ((pr == c) ? 1.0 : x);
+    V[(size_t)lr * LDV + c] = (c >= nref || pr < c) ? 0.0 : ((pr == c) ? 1.0 : x);
   }
   if (CS > 1) cluster.sync();   // no CTA may exit while its shared memory can still be written remotely
 }
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
   }
   // ---- outputs: the factored block in place (R over V), V as a dense operand
   if (valid) {
-    double* V = a.V + (size_t)t * n * NB + (size_t)(r0 + pr) * NB;
+    double* V = a.V + (size_t)t * n * LDV + (size_t)(r0 + pr) * LDV;
 #pragma unroll
     for (int c = 0; c < NB; c += 2) {
       *reinterpret_cast<double2*>(rowg + c) = make_double2(P[c], P[c + 1]);
@@ -492,12 +503,15 @@ constexpr int SY_MAXSPLIT = 4;      // split-K factor of the symm (partial Y buf
 
 struct SymmArgs {
   const double* A; size_t strideA; int ldk;
-  const double* V;   // T x n x NB
+  const double* V;   // T x n x LDV, offset to this panel's column block
   double* Y;         // T x n x NB
   const double* Bq;  // T x n x ldb or null
   int ldb, nz;
   double* Mpart;     // T x nblk x NB x NB    (nblk = row blocks x splits)
   double* Zpart;     // T x nzblk x NB x SY_ZW (nzblk = row blocks)
+  // second panel of a deferred-update group: the first panel's V_a, W_a (T x n x LDV, column block 0) and the
+  // partials of G1 = W_a^T V, G2 = V_a^T V (T x nzblk x 2 x NB x NB); null otherwise
+  const double* Va; const double* Wa; double* Gpart;
   int n, r0, nblk, nzblk;
 };
 
@@ -538,7 +552,7 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
   const int fr = lane >> 2, fk = lane & 3;
   const int n = a.n, r0 = a.r0, ldk = a.ldk;
   const double* A = a.A + (size_t)t * a.strideA;
-  const double* V = a.V + (size_t)t * n * NB;
+  const double* V = a.V + (size_t)t * n * LDV;
   const int i0 = r0 + SY_BM * bx;
   const int m = n - r0;
   const int nq = (m + SY_KC - 1) / SY_KC;
@@ -588,7 +602,7 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
     for (int s = 0; s < KC / 16; ++s) {
       const int row = vrow + 16 * s;
       const bool ok = (j0 + row < n);
-      cp_async16(vs + row * SY_SV + 2 * vpart, ok ? V + (size_t)(j0 + row) * NB + 2 * vpart : V, ok);
+      cp_async16(vs + row * SY_SV + 2 * vpart, ok ? V + (size_t)(j0 + row) * LDV + 2 * vpart : V, ok);
     }
   };
 
@@ -638,7 +652,7 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
   }
   for (int e = tid; e < SY_BM * NB; e += 256) {
     const int rl = e / NB, c = e % NB;
-    Vs[rl * (NB + 1) + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * NB + c] : 0.0;
+    Vs[rl * (NB + 1) + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
   }
   __syncthreads();
   {
@@ -651,6 +665,28 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
     double* Mp = a.Mpart + ((size_t)t * a.nblk + bx * S + sp) * NB * NB;
 #pragma unroll
     for (int u = 0; u < 4; ++u) Mp[(wid + 8 * u) * NB + lane] = mp[u];
+  }
+  // deferred-update group, second panel: partials of G1 = W_a^T V and G2 = V_a^T V over this row block
+  if (a.Gpart && sp == 0) {
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const double* src = (which == 0 ? a.Wa : a.Va) + (size_t)t * n * LDV;
+      __syncthreads();                       // Ys (Y rows, then W_a rows) has been consumed
+      for (int e = tid; e < SY_BM * NB; e += 256) {
+        const int rl = e / NB, c = e % NB;
+        Ys[rl * (NB + 1) + c] = (i0 + rl < n) ? src[(size_t)(i0 + rl) * LDV + c] : 0.0;
+      }
+      __syncthreads();
+      double gp[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int rl = 0; rl < SY_BM; ++rl) {
+        const double vv = Vs[rl * (NB + 1) + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gp[u] = fma(Ys[rl * (NB + 1) + wid + 8 * u], vv, gp[u]);
+      }
+      double* Gp = a.Gpart + (((size_t)t * a.nzblk + bx) * 2 + which) * NB * NB;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Gp[(wid + 8 * u) * NB + lane] = gp[u];
+    }
   }
   if (a.Bq && a.nz > 0 && sp == 0) {
     const double* Bq = a.Bq + (size_t)t * n * a.ldb;
@@ -673,10 +709,11 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
 
 // ------------------------------------------------------------------ fixed-order reduction of the partials
 struct ReduceArgs {
-  const double* Mpart; const double* Zpart;
+  const double* Mpart; const double* Zpart; const double* Gpart;
   double* Mred;   // T x NB x NB
   double* Zred;   // T x NB x SY_ZW
-  int nblk, nzblk, has_z;
+  double* Gred;   // T x 2 x NB x NB
+  int nblk, nzblk, has_z, has_g;
 };
 
 __global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
@@ -688,254 +725,312 @@ __global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
     double s = 0.0;
     for (int b = 0; b < a.nblk; ++b) s += p[(size_t)b * NM];
     a.Mred[(size_t)t * NM + e] = s;
-  } else if (e < NM + NZ && a.has_z) {
+  } else if (e < NM + NZ) {
+    if (!a.has_z) return;
     const int ez = e - NM;
     const double* p = a.Zpart + (size_t)t * a.nzblk * NZ + ez;
     double s = 0.0;
     for (int b = 0; b < a.nzblk; ++b) s += p[(size_t)b * NZ];
     a.Zred[(size_t)t * NZ + ez] = s;
+  } else if (e < NM + NZ + 2 * NM && a.has_g) {
+    const int eg = e - NM - NZ;
+    const double* p = a.Gpart + (size_t)t * a.nzblk * 2 * NM + eg;
+    double s = 0.0;
+    for (int b = 0; b < a.nzblk; ++b) s += p[(size_t)b * 2 * NM];
+    a.Gred[(size_t)t * 2 * NM + eg] = s;
   }
 }
 
-// ------------------------------------------------------------------ W and the Z-block update
+// ------------------------------------------------------------------ the panel's small matrices (one CTA per matrix)
+//   M  = V^T Y            (as reduced; second panel of a group: M -= G2^T G1 + G1^T G2, the stale-matrix correction)
+//   TM = T^T M,  TZ = T^T (V^T B)
+// computed ONCE per matrix and panel (the row-block kernels below only stream)
+struct SmallArgs {
+  const double* Tf; size_t tf_stride;      // this panel's slot
+  const double* Mred; const double* Zred; const double* Gred;
+  double* TM;     // T x NB x NB
+  double* TZ;     // T x NB x SY_ZW
+  int has_z, has_g;
+};
+
+__global__ void __launch_bounds__(256) smallmat_kernel(SmallArgs a) {
+  __shared__ double Ts[NB * (NB + 1)], Ms[NB * (NB + 1)], G1s[NB * (NB + 1)], G2s[NB * (NB + 1)];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double* Tf = a.Tf + (size_t)t * a.tf_stride;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e / NB, c = e % NB;
+    Ts[r * (NB + 1) + c] = Tf[e];
+    Ms[r * (NB + 1) + c] = a.Mred[(size_t)t * NB * NB + e];
+    if (a.has_g) {
+      G1s[r * (NB + 1) + c] = a.Gred[(size_t)t * 2 * NB * NB + e];
+      G2s[r * (NB + 1) + c] = a.Gred[(size_t)t * 2 * NB * NB + NB * NB + e];
+    }
+  }
+  __syncthreads();
+  if (a.has_g) {
+    // M[r][c] -= sum_k G2[k][r] G1[k][c] + G1[k][r] G2[k][c]      (rows r = wid + 8 u, column c = lane)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+      const double g1c = G1s[k * (NB + 1) + lane], g2c = G2s[k * (NB + 1) + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        acc[u] = fma(G2s[k * (NB + 1) + wid + 8 * u], g1c, fma(G1s[k * (NB + 1) + wid + 8 * u], g2c, acc[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Ms[(wid + 8 * u) * (NB + 1) + lane] -= acc[u];
+    __syncthreads();
+  }
+  {
+    // TM[r][c] = sum_k T[k][r] M[k][c]   (T upper triangular with explicit zeros)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+      const double mv = Ms[k * (NB + 1) + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fma(Ts[k * (NB + 1) + wid + 8 * u], mv, acc[u]);
+    }
+    double* TM = a.TM + (size_t)t * NB * NB;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) TM[(wid + 8 * u) * NB + lane] = acc[u];
+  }
+  if (a.has_z) {
+    const double* Zr = a.Zred + (size_t)t * NB * SY_ZW;
+    double* TZ = a.TZ + (size_t)t * NB * SY_ZW;
+    const int z = tid & 127, hg = tid >> 7;
+    double acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[u] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < NB; ++k) {
+      const double zv = Zr[k * SY_ZW + z];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc[u] = fma(Ts[k * (NB + 1) + hg + 2 * u], zv, acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) TZ[(hg + 2 * u) * SY_ZW + z] = acc[u];
+  }
+}
+
+// ------------------------------------------------------------------ W = (Y - 1/2 V T^T M) T  per 64-row block
 struct WformArgs {
-  const double* V; const double* Y; double* W;   // T x n x NB  (Y: nsplit partial buffers of T x n x NB)
+  const double* V;      // T x n x LDV, this panel's column block
+  const double* Y;      // nsplit partial buffers of T x n x NB
+  double* W;            // T x n x LDV, this panel's column block
   int nsplit, T;
   const double* Tf; size_t tf_stride;            // this panel's slot
-  const double* Mred; const double* Zred;
-  double* Bq; int ldb, nz;
+  const double* TM;     // T x NB x NB
+  const double* Gred;   // T x 2 x NB x NB  (G1, G2) with Va / Wa: stale-matrix correction, or null
+  const double* Va; const double* Wa;            // T x n x LDV, column block 0
   int n, r0;
 };
 
 constexpr int WF_BM = 64;
-constexpr size_t WF_SMEM = (3 * NB * (NB + 1) + NB * SY_ZW + 2 * WF_BM * (NB + 1)) * sizeof(double);
+constexpr int WF_RS = NB + 1;
+constexpr size_t WF_SMEM = (size_t)(2 * NB * WF_RS + 2 * WF_BM * WF_RS) * sizeof(double);
+
+// out[r][c] (rows wid + 8 q, column lane) += sign * sum_k R[r][k] Mx[k][c]
+__device__ __forceinline__ void wf_mac(double (&acc)[WF_BM / 8], const double* __restrict__ R,
+                                       const double* __restrict__ Mx, int wid, int lane, double sign) {
+  double part[WF_BM / 8];
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) part[q] = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < NB; ++k) {
+    const double mv = Mx[k * WF_RS + lane];
+#pragma unroll
+    for (int q = 0; q < WF_BM / 8; ++q) part[q] = fma(R[(wid + 8 * q) * WF_RS + k], mv, part[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) acc[q] = fma(sign, part[q], acc[q]);
+}
 
 __global__ void __launch_bounds__(256) wform_kernel(WformArgs a) {
   extern __shared__ __align__(16) double smem[];
-  double* Ts = smem;                        // NB x (NB + 1)
-  double* TM = Ts + NB * (NB + 1);          // M, then T^T M
-  double* Ms = TM + NB * (NB + 1);          // (unused half kept for layout compatibility)
-  double* TZ = Ms + NB * (NB + 1);          // NB x SY_ZW: V^T B, then T^T V^T B
-  double* Vs = TZ + NB * SY_ZW;             // WF_BM x (NB + 1)
-  double* Xs = Vs + WF_BM * (NB + 1);
+  double* Mx0 = smem;                       // NB x WF_RS  (two matrix slots, two row-operand slots: every phase
+  double* Mx1 = Mx0 + NB * WF_RS;           //  reads one pair while the next pair is being filled)
+  double* R0 = Mx1 + NB * WF_RS;            // WF_BM x WF_RS
+  double* R1 = R0 + WF_BM * WF_RS;
   const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = a.n, i0 = a.r0 + WF_BM * blockIdx.x;
+  const bool corr = a.Gred != nullptr;
   const double* Tf = a.Tf + (size_t)t * a.tf_stride;
-  const double* V = a.V + (size_t)t * n * NB;
-  const double* Y = a.Y + (size_t)t * n * NB;
-  double* W = a.W + (size_t)t * n * NB;
-  const bool hz = a.Bq && a.nz > 0;
-  for (int e = tid; e < NB * NB; e += 256) {
-    Ts[(e / NB) * (NB + 1) + (e % NB)] = Tf[e];
-    TM[(e / NB) * (NB + 1) + (e % NB)] = a.Mred[(size_t)t * NB * NB + e];
+  const double* TM = a.TM + (size_t)t * NB * NB;
+  const double* V = a.V + (size_t)t * n * LDV;
+  double* W = a.W + (size_t)t * n * LDV;
+  auto load_mat = [&](double* dst, const double* src) {
+    for (int e = tid; e < NB * NB; e += 256) dst[(e / NB) * WF_RS + (e % NB)] = src[e];
+  };
+  auto load_rows = [&](double* dst, const double* src) {      // src: T x n x LDV operand, rows i0 ..
+    for (int e = tid; e < WF_BM * NB; e += 256) {
+      const int rl = e / NB, c = e % NB;
+      dst[rl * WF_RS + c] = (i0 + rl < n) ? src[(size_t)(i0 + rl) * LDV + c] : 0.0;
+    }
+  };
+  // accumulators start at the summed split-K partials of Y
+  double acc[WF_BM / 8];
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) {
+    const int i = i0 + wid + 8 * q;
+    double yv = 0.0;
+    if (i < n)
+      for (int sp = 0; sp < a.nsplit; ++sp) yv += a.Y[((size_t)sp * a.T + t) * n * NB + (size_t)i * NB + lane];
+    acc[q] = yv;
   }
-  if (hz) {
-    const double* Zr = a.Zred + (size_t)t * NB * SY_ZW;
-    for (int e = tid; e < NB * SY_ZW; e += 256) TZ[e] = Zr[e];
+  if (corr) {
+    const double* G = a.Gred + (size_t)t * 2 * NB * NB;
+    load_mat(Mx0, G);                                     // G1 = W_a^T V
+    load_rows(R0, a.Va + (size_t)t * n * LDV);
+    load_mat(Mx1, G + NB * NB);                           // G2 = V_a^T V
+    load_rows(R1, a.Wa + (size_t)t * n * LDV);
+    __syncthreads();
+    wf_mac(acc, R0, Mx0, wid, lane, -1.0);                // Y -= V_a G1
+    wf_mac(acc, R1, Mx1, wid, lane, -1.0);                // Y -= W_a G2
+    __syncthreads();
   }
+  load_mat(Mx0, TM);
+  load_rows(R0, V);
+  load_mat(Mx1, Tf);
+  __syncthreads();
+  wf_mac(acc, R0, Mx0, wid, lane, -0.5);                  // X1 = Y - 1/2 V (T^T M)
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) R1[(wid + 8 * q) * WF_RS + lane] = acc[q];
+  __syncthreads();
+  double wv[WF_BM / 8];
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) wv[q] = 0.0;
+  wf_mac(wv, R1, Mx1, wid, lane, 1.0);                    // W = X1 T
+#pragma unroll
+  for (int q = 0; q < WF_BM / 8; ++q) {
+    const int i = i0 + wid + 8 * q;
+    if (i < n) W[(size_t)i * LDV + lane] = wv[q];
+  }
+}
+
+// ------------------------------------------------------------------ B -= V (T^T V^T B)  per 64-row block
+struct ZupdArgs {
+  const double* V;      // T x n x LDV, this panel's column block
+  const double* TZ;     // T x NB x SY_ZW
+  double* Bq; int ldb, nz;
+  int n, r0;
+};
+constexpr size_t ZU_SMEM = (size_t)(NB * SY_ZW + WF_BM * WF_RS) * sizeof(double);
+
+__global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* TZs = smem;                       // NB x SY_ZW
+  double* Vs = TZs + NB * SY_ZW;            // WF_BM x WF_RS
+  const int t = blockIdx.y, tid = threadIdx.x;
+  const int n = a.n, i0 = a.r0 + WF_BM * blockIdx.x;
+  const double* V = a.V + (size_t)t * n * LDV;
+  const double* TZ = a.TZ + (size_t)t * NB * SY_ZW;
+  double* Bq = a.Bq + (size_t)t * n * a.ldb;
+  const int z = tid & 127, hg = tid >> 7;
+  for (int e = tid; e < NB * SY_ZW; e += 256) TZs[e] = TZ[e];
   for (int e = tid; e < WF_BM * NB; e += 256) {
     const int rl = e / NB, c = e % NB;
-    const bool ok = i0 + rl < n;
-    Vs[rl * (NB + 1) + c] = ok ? V[(size_t)(i0 + rl) * NB + c] : 0.0;
-    double yv = 0.0;
-    if (ok)
-      for (int sp = 0; sp < a.nsplit; ++sp) yv += Y[(size_t)sp * a.T * n * NB + (size_t)(i0 + rl) * NB + c];
-    Xs[rl * (NB + 1) + c] = yv;
+    Vs[rl * WF_RS + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
   }
   __syncthreads();
-  // T^T M and T^T (V^T B) in registers, then in place:  out[a][c] = sum_{k <= a} T[k][a] in[k][c].  T is stored with
-  // explicit zeros below the diagonal, so every loop below runs over all k with several independent accumulation
-  // chains per thread (the triangular, one-chain-at-a-time version was latency bound: 70 us per CTA)
-  double tm[4] = {0.0, 0.0, 0.0, 0.0}, tz[16];
+  if (z >= a.nz) return;
+  // batches of 8 rows: all loads of a batch in flight before its first store, 8 independent chains
+#pragma unroll 1
+  for (int ub = 0; ub < WF_BM / 2; ub += 8) {
+    double bv[8], sv[8];
 #pragma unroll
-  for (int u = 0; u < 16; ++u) tz[u] = 0.0;
-  {
-    const int z = tid & 127, hg = tid >> 7;
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + hg + 2 * (ub + u);
+      bv[u] = (i < n) ? Bq[(size_t)i * a.ldb + z] : 0.0;
+      sv[u] = 0.0;
+    }
 #pragma unroll 4
     for (int k = 0; k < NB; ++k) {
-      const double mv = TM[k * (NB + 1) + lane];
+      const double zv = TZs[k * SY_ZW + z];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) tm[u] = fma(Ts[k * (NB + 1) + wid + 8 * u], mv, tm[u]);
-      if (hz) {
-        const double zv = TZ[k * SY_ZW + z];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) tz[u] = fma(Ts[k * (NB + 1) + hg + 2 * u], zv, tz[u]);
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < 4; ++u) TM[(wid + 8 * u) * (NB + 1) + lane] = tm[u];
-  if (hz) {
-    const int z = tid & 127, hg = tid >> 7;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) TZ[(hg + 2 * u) * SY_ZW + z] = tz[u];
-  }
-  __syncthreads();
-  // X1 = Y - 1/2 V TM   (rows wid + 8 q, 8 independent chains)
-  double x1[WF_BM / 8];
-#pragma unroll
-  for (int q = 0; q < WF_BM / 8; ++q) x1[q] = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < NB; ++k) {
-    const double tv = TM[k * (NB + 1) + lane];
-#pragma unroll
-    for (int q = 0; q < WF_BM / 8; ++q) x1[q] = fma(Vs[(wid + 8 * q) * (NB + 1) + k], tv, x1[q]);
-  }
-#pragma unroll
-  for (int q = 0; q < WF_BM / 8; ++q) x1[q] = Xs[(wid + 8 * q) * (NB + 1) + lane] - 0.5 * x1[q];
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < WF_BM / 8; ++q) Xs[(wid + 8 * q) * (NB + 1) + lane] = x1[q];
-  __syncthreads();
-  // W = X1 T
-  {
-    double wv[WF_BM / 8];
-#pragma unroll
-    for (int q = 0; q < WF_BM / 8; ++q) wv[q] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < NB; ++k) {
-      const double tv = Ts[k * (NB + 1) + lane];
-#pragma unroll
-      for (int q = 0; q < WF_BM / 8; ++q) wv[q] = fma(Xs[(wid + 8 * q) * (NB + 1) + k], tv, wv[q]);
+      for (int u = 0; u < 8; ++u) sv[u] = fma(Vs[(hg + 2 * (ub + u)) * WF_RS + k], zv, sv[u]);
     }
 #pragma unroll
-    for (int q = 0; q < WF_BM / 8; ++q) {
-      const int rl = wid + 8 * q;
-      if (i0 + rl < n) W[(size_t)(i0 + rl) * NB + lane] = wv[q];
-    }
-  }
-  if (hz) {
-    double* Bq = a.Bq + (size_t)t * n * a.ldb;
-    const int z = tid & 127, hg = tid >> 7;
-    if (z < a.nz) {
-      // batches of 8 rows: all loads in flight before the first store, 8 independent chains
-      for (int rb = 0; rb < WF_BM; rb += 16) {
-        double bv[8], sv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + rb + hg + 2 * u;
-          bv[u] = (i < n) ? Bq[(size_t)i * a.ldb + z] : 0.0;
-          sv[u] = 0.0;
-        }
-#pragma unroll 4
-        for (int k = 0; k < NB; ++k) {
-          const double zv = TZ[k * SY_ZW + z];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) sv[u] = fma(Vs[(rb + hg + 2 * u) * (NB + 1) + k], zv, sv[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int rl = rb + hg + 2 * u;
-          if (i0 + rl < n) Bq[(size_t)(i0 + rl) * a.ldb + z] = bv[u] - sv[u];
-        }
-      }
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + hg + 2 * (ub + u);
+      if (i < n) Bq[(size_t)i * a.ldb + z] = bv[u] - sv[u];
     }
   }
 }
 
-// ------------------------------------------------------------------ A22 -= V W^T + W V^T  (lower tiles)
-constexpr int S2_BM = 128, S2_BN = 64, S2_K = 2 * NB;
-constexpr int S2_S = S2_K + 4;
+// ------------------------------------------------------------------ thin update of the next panel's block column
+// Second panel of a deferred-update group (columns c0 .. c0+NB-1, rows >= c0): bring the block column up to date with
+// the first panel's reflector before its QR,  A[i][j] -= V_a[i] . W_a[j] + W_a[i] . V_a[j]   (lower part, i >= j).
+struct PupdArgs {
+  double* A; size_t strideA; int ldk;
+  const double* Va; const double* Wa;     // T x n x LDV, column block 0
+  int n, c0;
+};
+constexpr int PU_BM = 64;
+constexpr size_t PU_SMEM = (size_t)(2 * PU_BM * WF_RS + 2 * NB * WF_RS) * sizeof(double);
+
+__global__ void __launch_bounds__(256) panel_update_kernel(PupdArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* VI = smem;                        // PU_BM x WF_RS
+  double* WI = VI + PU_BM * WF_RS;
+  double* VJ = WI + PU_BM * WF_RS;          // NB x WF_RS  (rows c0 .. c0+NB-1 of V_a / W_a)
+  double* WJ = VJ + NB * WF_RS;
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = a.n, c0 = a.c0, i0 = c0 + PU_BM * blockIdx.x;
+  const double* Va = a.Va + (size_t)t * n * LDV;
+  const double* Wa = a.Wa + (size_t)t * n * LDV;
+  double* A = a.A + (size_t)t * a.strideA;
+  for (int e = tid; e < PU_BM * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    const bool ok = i0 + rl < n;
+    VI[rl * WF_RS + c] = ok ? Va[(size_t)(i0 + rl) * LDV + c] : 0.0;
+    WI[rl * WF_RS + c] = ok ? Wa[(size_t)(i0 + rl) * LDV + c] : 0.0;
+  }
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    const bool ok = c0 + rl < n;
+    VJ[rl * WF_RS + c] = ok ? Va[(size_t)(c0 + rl) * LDV + c] : 0.0;
+    WJ[rl * WF_RS + c] = ok ? Wa[(size_t)(c0 + rl) * LDV + c] : 0.0;
+  }
+  __syncthreads();
+  // thread: column j = c0 + lane, rows i0 + wid + 8 q
+  double acc[PU_BM / 8];
+#pragma unroll
+  for (int q = 0; q < PU_BM / 8; ++q) acc[q] = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < NB; ++k) {
+    const double wj = WJ[lane * WF_RS + k], vj = VJ[lane * WF_RS + k];
+#pragma unroll
+    for (int q = 0; q < PU_BM / 8; ++q)
+      acc[q] = fma(VI[(wid + 8 * q) * WF_RS + k], wj, fma(WI[(wid + 8 * q) * WF_RS + k], vj, acc[q]));
+  }
+  const int j = c0 + lane;
+#pragma unroll
+  for (int q = 0; q < PU_BM / 8; ++q) {
+    const int i = i0 + wid + 8 * q;
+    if (i < n && j < n && j <= i) A[(size_t)i * a.ldk + j] -= acc[q];
+  }
+}
+
+// ------------------------------------------------------------------ A22 -= sum_q V_q W_q^T + W_q V_q^T  (lower tiles)
+// Row-persistent DMMA kernel: one CTA keeps Z_I = [V_I | W_I] (all G panels of the group: K = 2 G NB columns) of its
+// 128-row block in shared memory and walks a chunk of BN-column tiles of that block row; the next tile's
+// Z'_J = [W_J | V_J] (cp.async, double buffered) and its A values (registers) are fetched while the current tile is on
+// the tensor cores; accumulators start at -A, the result is stored as -acc.
+constexpr int S3_BM = 128;   // tile rows
 
 struct Syr2kArgs {
   double* A; size_t strideA; int ldk;
-  const double* V; const double* W;
+  const double* V; const double* W;   // T x n x LDV, column blocks 0 .. G-1
   int n, r0;
 };
 
-__global__ void __launch_bounds__(256, 2) syr2k_kernel(Syr2kArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  const int t = blockIdx.z;
-  const int n = a.n, r0 = a.r0, ldk = a.ldk;
-  const int i0 = r0 + S2_BM * blockIdx.y, j0 = r0 + S2_BN * blockIdx.x;
-  if (j0 > i0 + S2_BM - 1) return;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int fr = lane >> 2, fk = lane & 3;
-  double* A = a.A + (size_t)t * a.strideA;
-  const double* V = a.V + (size_t)t * n * NB;
-  const double* W = a.W + (size_t)t * n * NB;
-  double* As = smem;                     // S2_BM x S2_S : [V_I | W_I]
-  double* Bs = As + S2_BM * S2_S;        // S2_BN x S2_S : [W_J | V_J]
-#pragma unroll
-  for (int s = 0; s < 16; ++s) {
-    const int c = tid + 256 * s, row = c >> 5, part = c & 31;
-    const bool ok = i0 + row < n;
-    const double* base = (part < 16) ? V : W;
-    const double* src = ok ? base + (size_t)(i0 + row) * NB + 2 * (part & 15) : base;
-    cp_async16(As + row * S2_S + 2 * part, src, ok);
-  }
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const int c = tid + 256 * s, row = c >> 5, part = c & 31;
-    const bool ok = j0 + row < n;
-    const double* base = (part < 16) ? W : V;
-    const double* src = ok ? base + (size_t)(j0 + row) * NB + 2 * (part & 15) : base;
-    cp_async16(Bs + row * S2_S + 2 * part, src, ok);
-  }
-  cp_async_commit();
-  const int wm = wid >> 1, wn = wid & 1;   // 4 x 2 warps, warp tile 32 x 32
-  // accumulators start at -A (loaded while the operand copies are in flight); the result is stored as -acc
-  double acc[4][4][2];
-#pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int i = i0 + 32 * wm + 8 * x + fr;
-#pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const int j = j0 + 32 * wn + 8 * y + 2 * fk;
-      const double* p = A + (size_t)i * ldk + j;
-      double2 o = make_double2(0.0, 0.0);
-      if (i < n) {
-        if (j + 1 <= i) o = ldcg2(reinterpret_cast<const double2*>(p));
-        else if (j <= i) o.x = ldcg(p);
-      }
-      acc[x][y][0] = -o.x;
-      acc[x][y][1] = -o.y;
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-  {
-    const double* ap = As + (32 * wm + fr) * S2_S + fk;
-    const double* bp = Bs + (32 * wn + fr) * S2_S + fk;
-#pragma unroll 4
-    for (int kk = 0; kk < S2_K; kk += 4) {
-      double af[4], bf[4];
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        af[x] = ap[8 * x * S2_S + kk];
-        bf[x] = bp[8 * x * S2_S + kk];
-      }
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-    }
-  }
-#pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int i = i0 + 32 * wm + 8 * x + fr;
-    if (i < n) {
-#pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        const int j = j0 + 32 * wn + 8 * y + 2 * fk;
-        double* p = A + (size_t)i * ldk + j;
-        if (j + 1 <= i) *reinterpret_cast<double2*>(p) = make_double2(-acc[x][y][0], -acc[x][y][1]);
-        else if (j <= i) p[0] = -acc[x][y][0];
-      }
-    }
-  }
-}
-
-// ---- row-persistent variant: one CTA keeps [V_I | W_I] of its 128-row block in shared memory and walks a chunk of
-// 32-column tiles of that block row; the next tile's [W_J | V_J] (cp.async, double buffered) and its A values
-// (registers) are fetched while the current tile is on the tensor cores.
-constexpr int S3_BM = 128;   // tile rows
-
-// BN = tile columns (32: two CTAs per SM, 64: one CTA per SM with twice the work per barrier), CH = tiles per CTA
-template <int BN, int CH>
-__global__ void __launch_bounds__(256, BN == 32 ? 2 : 1) syr2k_row_kernel(Syr2kArgs a) {
-  constexpr int NY = BN / 16;   // 8-column fragments per warp
+// BN = tile columns, CH = tiles per CTA, G = panels in the update (K = 2 G NB)
+template <int BN, int CH, int G>
+__global__ void __launch_bounds__(256, 1) syr2k_row_kernel(Syr2kArgs a) {
+  constexpr int NY = BN / 16;          // 8-column fragments per warp
+  constexpr int KT = 2 * G * NB;       // K of the update
+  constexpr int SS = KT + 4;           // shared-memory row stride (== 4 mod 8: conflict-free fragment loads)
+  constexpr int CPR = KT / 2;          // 16-byte chunks per operand row
   extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.z;
   const int n = a.n, r0 = a.r0, ldk = a.ldk;
@@ -947,28 +1042,24 @@ __global__ void __launch_bounds__(256, BN == 32 ? 2 : 1) syr2k_row_kernel(Syr2kA
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   double* A = a.A + (size_t)t * a.strideA;
-  const double* V = a.V + (size_t)t * n * NB;
-  const double* W = a.W + (size_t)t * n * NB;
-  double* As = smem;                      // S3_BM x S2_S : [V_I | W_I]
-  double* Bs = As + S3_BM * S2_S;         // 2 x BN x S2_S : [W_J | V_J]
+  const double* V = a.V + (size_t)t * n * LDV;
+  const double* W = a.W + (size_t)t * n * LDV;
+  double* As = smem;                      // S3_BM x SS : [V_I | W_I]
+  double* Bs = As + S3_BM * SS;           // 2 x BN x SS : [W_J | V_J]
   const int wm = wid >> 1, wn = wid & 1;  // 4 x 2 warps, warp tile 32 x BN/2
-#pragma unroll
-  for (int s = 0; s < 16; ++s) {
-    const int c = tid + 256 * s, row = c >> 5, part = c & 31;
-    const bool ok = i0 + row < n;
-    const double* base = (part < 16) ? V : W;
-    cp_async16(As + row * S2_S + 2 * part, ok ? base + (size_t)(i0 + row) * NB + 2 * (part & 15) : base, ok);
-  }
-  auto issue_b = [&](int jt) {
-    double* dst = Bs + (size_t)((jt - jt_lo) & 1) * BN * S2_S;
-    const int j0 = r0 + BN * jt;
-#pragma unroll
-    for (int s = 0; s < BN / 8; ++s) {
-      const int c = tid + 256 * s, row = c >> 5, part = c & 31;
-      const bool ok = j0 + row < n;
-      const double* base = (part < 16) ? W : V;
-      cp_async16(dst + row * S2_S + 2 * part, ok ? base + (size_t)(j0 + row) * NB + 2 * (part & 15) : base, ok);
+  // operand row: chunks 0 .. CPR/2-1 from the first array, the rest from the second (G NB columns each)
+  auto stage_rows = [&](double* dst, int row0, int rows, const double* first, const double* second) {
+    for (int c = tid; c < rows * CPR; c += 256) {
+      const int row = c / CPR, part = c % CPR;
+      const bool ok = row0 + row < n;
+      const double* base = (part < CPR / 2) ? first : second;
+      const int col = 2 * (part % (CPR / 2));
+      cp_async16(dst + row * SS + 2 * part, ok ? base + (size_t)(row0 + row) * LDV + col : base, ok);
     }
+  };
+  stage_rows(As, i0, S3_BM, V, W);
+  auto issue_b = [&](int jt) {
+    stage_rows(Bs + (size_t)((jt - jt_lo) & 1) * BN * SS, r0 + BN * jt, BN, W, V);
   };
   double nxt[4][NY][2];
   const size_t rowstep = (size_t)8 * ldk;
@@ -1007,7 +1098,7 @@ __global__ void __launch_bounds__(256, BN == 32 ? 2 : 1) syr2k_row_kernel(Syr2kA
   issue_b(jt_lo);
   cp_async_commit();
   load_a(jt_lo);
-  const double* ap = As + (32 * wm + fr) * S2_S + fk;
+  const double* ap = As + (32 * wm + fr) * SS + fk;
   for (int jt = jt_lo; jt < jt_hi; ++jt) {
     cp_async_wait<0>();
     __syncthreads();
@@ -1019,14 +1110,14 @@ __global__ void __launch_bounds__(256, BN == 32 ? 2 : 1) syr2k_row_kernel(Syr2kA
 #pragma unroll
       for (int y = 0; y < NY; ++y) { acc[x][y][0] = -nxt[x][y][0]; acc[x][y][1] = -nxt[x][y][1]; }
     if (jt + 1 < jt_hi) load_a(jt + 1);
-    const double* bp = Bs + (size_t)((jt - jt_lo) & 1) * BN * S2_S + ((BN / 2) * wn + fr) * S2_S + fk;
+    const double* bp = Bs + (size_t)((jt - jt_lo) & 1) * BN * SS + ((BN / 2) * wn + fr) * SS + fk;
 #pragma unroll 4
-    for (int kk = 0; kk < S2_K; kk += 4) {
+    for (int kk = 0; kk < KT; kk += 4) {
       double af[4], bf[NY];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) af[x] = ap[8 * x * S2_S + kk];
+      for (int x = 0; x < 4; ++x) af[x] = ap[8 * x * SS + kk];
 #pragma unroll
-      for (int y = 0; y < NY; ++y) bf[y] = bp[8 * y * S2_S + kk];
+      for (int y = 0; y < NY; ++y) bf[y] = bp[8 * y * SS + kk];
 #pragma unroll
       for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -1058,6 +1149,8 @@ __global__ void __launch_bounds__(256, BN == 32 ? 2 : 1) syr2k_row_kernel(Syr2kA
     }
   }
 }
+template <int BN, int G>
+constexpr size_t syr2k_smem() { return (size_t)(S3_BM + 2 * BN) * (2 * G * NB + 4) * sizeof(double); }
 
 // ------------------------------------------------------------------ band extraction / padding
 // bandS[i][d] = T_b(i, i-d), d = 0..NB  (stride CHD_BAND_LD);  bandW: the same with room for the bulges
@@ -1210,31 +1303,38 @@ size_t band_workspace(const Plan* pl, int T) {
   const size_t n = pl->n;
   const size_t nblk = (n + SY_BM - 1) / SY_BM;
   size_t b = 0;
-  b += (2 + SY_MAXSPLIT) * align_up(T * n * NB * sizeof(double), 256);       // V, W, Y (split-K partials)
+  b += 2 * align_up(T * n * LDV * sizeof(double), 256);                      // V, W (KD panels side by side)
+  b += SY_MAXSPLIT * align_up(T * n * NB * sizeof(double), 256);             // Y (split-K partials)
   b += align_up((size_t)T * (band_npanels(pl->n) + 1) * NB * NB * sizeof(double), 256);   // T factors
   b += align_up((size_t)T * nblk * SY_MAXSPLIT * NB * NB * sizeof(double), 256);   // Mpart
   b += align_up((size_t)T * nblk * NB * SY_ZW * sizeof(double), 256);        // Zpart
-  b += align_up((size_t)T * NB * NB * sizeof(double), 256);                  // Mred
-  b += align_up((size_t)T * NB * SY_ZW * sizeof(double), 256);               // Zred
+  b += align_up((size_t)T * nblk * 2 * NB * NB * sizeof(double), 256);       // Gpart
+  b += 2 * align_up((size_t)T * NB * NB * sizeof(double), 256);              // Mred, TM
+  b += 2 * align_up((size_t)T * NB * SY_ZW * sizeof(double), 256);           // Zred, TZ
+  b += align_up((size_t)T * 2 * NB * NB * sizeof(double), 256);              // Gred
   b += align_up(T * n * sizeof(double), 256);                                // v0
   b += align_up(T * sizeof(double), 256);                                    // tau0
   b += align_up((size_t)T * n * CHD_BAND_LD * sizeof(double), 256);          // bandS
   b += align_up((size_t)T * n * CHD_CHASE_LD * sizeof(double), 256);         // bandW
-  return b + 4096;
+  return b + 8192;
 }
 
 bool band_carve(const Plan* pl, int T, Carver& cv, BandBuffers& bb) {
   const size_t n = pl->n;
   const size_t nblk = (n + SY_BM - 1) / SY_BM;
-  bb.V = cv.take<double>(T * n * NB);
+  bb.V = cv.take<double>(T * n * LDV);
+  bb.W = cv.take<double>(T * n * LDV);
   bb.Y = cv.take<double>((size_t)SY_MAXSPLIT * T * n * NB);
-  bb.W = cv.take<double>(T * n * NB);
   bb.tf_stride = (size_t)(band_npanels(pl->n) + 1) * NB * NB;
   bb.Tf = cv.take<double>((size_t)T * bb.tf_stride);
   bb.Mpart = cv.take<double>((size_t)T * nblk * SY_MAXSPLIT * NB * NB);
   bb.Zpart = cv.take<double>((size_t)T * nblk * NB * SY_ZW);
+  bb.Gpart = cv.take<double>((size_t)T * nblk * 2 * NB * NB);
   bb.Mred = cv.take<double>((size_t)T * NB * NB);
+  bb.TM = cv.take<double>((size_t)T * NB * NB);
   bb.Zred = cv.take<double>((size_t)T * NB * SY_ZW);
+  bb.TZ = cv.take<double>((size_t)T * NB * SY_ZW);
+  bb.Gred = cv.take<double>((size_t)T * 2 * NB * NB);
   bb.v0 = cv.take<double>(T * n);
   bb.tau0 = cv.take<double>(T);
   bb.bandS = cv.take<double>((size_t)T * n * CHD_BAND_LD);
@@ -1242,32 +1342,34 @@ bool band_carve(const Plan* pl, int T, Carver& cv, BandBuffers& bb) {
   return cv.ok;
 }
 
-static int g_qr_max_cs = -1;
-
 static int qr_cluster_size(const Plan* pl, int m, int& RP, int& RS, size_t& smem) {
   // fixed part of the kernel's shared memory (doubles)
   const size_t fixed = 2 * QR_MAXCS * QR_XW + (QR_THREADS / 32) * QR_XW + 2 * QR_XW + 2 * NB + 2 * NB * QR_S;
   const size_t avail = (pl->smem_optin - fixed * sizeof(double)) / (QR_S * sizeof(double));
+  int max_cs = 8;
   {
     const char* e = getenv("CHD_QR_MAXCS");   // tuning / test switch: largest cluster the panel QR may use
-    g_qr_max_cs = e ? atoi(e) : 8;
-    if (g_qr_max_cs != 1 && g_qr_max_cs != 2 && g_qr_max_cs != 4 && g_qr_max_cs != 8 && g_qr_max_cs != 16)
-      g_qr_max_cs = 8;
+    const int v = e ? atoi(e) : 8;
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) max_cs = v;
   }
   int cs = 1;
-  while (cs < g_qr_max_cs && (m + cs - 1) / cs > 384) cs *= 2;
+  while (cs < max_cs && (m + cs - 1) / cs > 384) cs *= 2;
   RP = (m + cs - 1) / cs;
   RS = (int)((size_t)RP < avail ? (size_t)RP : avail);
   smem = (fixed + (size_t)RS * QR_S) * sizeof(double);
   return cs;
 }
 
-// Launches one panel's trailing work for V / Tf slot `slot` and trailing block starting at r0.
-static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B, int ldb, int nz, int r0, int slot,
-                           const BandBuffers& bb, cudaStream_t st) {
+// One slot's work between its reflectors (H_{-1} or a panel QR) and the group's trailing update:
+//   Y = A22 V (stale inside a group) -> partial sums -> small matrices -> W (with the stale-matrix corrections for the
+//   second panel of a group) and the Z-block update.  q = position of the slot in its group.
+static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int ldb, int nz, int r0, int slot, int q,
+                       const BandBuffers& bb, cudaStream_t st) {
   const int n = pl->n, m = n - r0;
   const size_t strideA = (size_t)n * ldk;
   const int nblk = (m + SY_BM - 1) / SY_BM;
+  const bool has_z = B && nz > 0, has_g = q > 0;
+  const double* Vq = bb.V + q * NB;
   int rc;
   // split-K so that the launch fills the machine (2 CTAs per SM) at least ~twice, while every CTA keeps a few chunks
   int S = 1;
@@ -1278,8 +1380,9 @@ static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B,
   }
   {
     SymmArgs a;
-    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Y = bb.Y; a.Bq = B; a.ldb = ldb; a.nz = nz;
+    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = Vq; a.Y = bb.Y; a.Bq = B; a.ldb = ldb; a.nz = nz;
     a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk * S; a.nzblk = nblk;
+    a.Va = has_g ? bb.V : nullptr; a.Wa = has_g ? bb.W : nullptr; a.Gpart = has_g ? bb.Gpart : nullptr;
     static const int kc = getenv("CHD_SYMM_KC") ? atoi(getenv("CHD_SYMM_KC")) : 32;
     if ((rc = profile_mark_begin(PROF_SYMM, st))) return rc;
     if (kc == 64)
@@ -1289,48 +1392,59 @@ static int trailing_launch(const Plan* pl, double* K, int ldk, int T, double* B,
     CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
   }
+  if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
   {
     ReduceArgs a;
-    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.Mred = bb.Mred; a.Zred = bb.Zred; a.nblk = nblk * S; a.nzblk = nblk;
-    a.has_z = (B && nz > 0) ? 1 : 0;
-    const int total = NB * NB + (a.has_z ? NB * SY_ZW : 0);
+    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.Gpart = bb.Gpart; a.Mred = bb.Mred; a.Zred = bb.Zred; a.Gred = bb.Gred;
+    a.nblk = nblk * S; a.nzblk = nblk; a.has_z = has_z ? 1 : 0; a.has_g = has_g ? 1 : 0;
+    const int total = NB * NB + NB * SY_ZW + (has_g ? 2 * NB * NB : 0);
     reduce_kernel<<<dim3((total + 255) / 256, T), 256, 0, st>>>(a);
     CHD_LAUNCHED();
   }
   {
-    WformArgs a;
-    a.V = bb.V; a.Y = bb.Y; a.W = bb.W; a.nsplit = S; a.T = T;
-    a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride;
-    a.Mred = bb.Mred; a.Zred = bb.Zred; a.Bq = B; a.ldb = ldb; a.nz = nz; a.n = n; a.r0 = r0;
-    if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
-    wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
+    SmallArgs a;
+    a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride; a.Mred = bb.Mred; a.Zred = bb.Zred;
+    a.Gred = bb.Gred; a.TM = bb.TM; a.TZ = bb.TZ; a.has_z = has_z ? 1 : 0; a.has_g = has_g ? 1 : 0;
+    smallmat_kernel<<<T, 256, 0, st>>>(a);
     CHD_LAUNCHED();
-    if ((rc = profile_mark_end(PROF_WFORM, st))) return rc;
   }
   {
-    Syr2kArgs a;
-    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.W = bb.W; a.n = n; a.r0 = r0;
-    // 0: one 128 x 64 tile per CTA; 1: row-persistent, 32-column tiles, two CTAs per SM; 2 (default): row-persistent,
-    // 64-column tiles, one CTA per SM (twice the tensor work per barrier: 5 % faster stage 1)
-    static const int variant = getenv("CHD_SYR2K") ? atoi(getenv("CHD_SYR2K")) : 2;
-    if ((rc = profile_mark_begin(PROF_SYR2K, st))) return rc;
-    if (variant == 0) {
-      const dim3 grid((m + S2_BN - 1) / S2_BN, (m + S2_BM - 1) / S2_BM, T);
-      syr2k_kernel<<<grid, 256, (S2_BM + S2_BN) * S2_S * sizeof(double), st>>>(a);
-    } else {
-      if (variant == 2) {
-        const int ntile = (m + 63) / 64;
-        const dim3 grid((ntile + 7) / 8, (m + S3_BM - 1) / S3_BM, T);
-        syr2k_row_kernel<64, 8><<<grid, 256, (S3_BM + 2 * 64) * S2_S * sizeof(double), st>>>(a);
-      } else {
-        const int ntile = (m + 31) / 32;
-        const dim3 grid((ntile + 15) / 16, (m + S3_BM - 1) / S3_BM, T);
-        syr2k_row_kernel<32, 16><<<grid, 256, (S3_BM + 2 * 32) * S2_S * sizeof(double), st>>>(a);
-      }
-    }
+    WformArgs a;
+    a.V = Vq; a.Y = bb.Y; a.W = bb.W + q * NB; a.nsplit = S; a.T = T;
+    a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride; a.TM = bb.TM;
+    a.Gred = has_g ? bb.Gred : nullptr; a.Va = bb.V; a.Wa = bb.W; a.n = n; a.r0 = r0;
+    wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
     CHD_LAUNCHED();
-    if ((rc = profile_mark_end(PROF_SYR2K, st))) return rc;
   }
+  if (has_z) {
+    ZupdArgs a;
+    a.V = Vq; a.TZ = bb.TZ; a.Bq = B; a.ldb = ldb; a.nz = nz; a.n = n; a.r0 = r0;
+    zupdate_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, ZU_SMEM, st>>>(a);
+    CHD_LAUNCHED();
+  }
+  if ((rc = profile_mark_end(PROF_WFORM, st))) return rc;
+  return CHD_OK;
+}
+
+// Trailing update of a group of G panels: A[r0:, r0:] -= sum_q V_q W_q^T + W_q V_q^T  (lower tiles)
+static int group_update_launch(const Plan* pl, double* K, int ldk, int T, int r0, int G, const BandBuffers& bb,
+                               cudaStream_t st) {
+  const int n = pl->n, m = n - r0;
+  Syr2kArgs a;
+  a.A = K; a.strideA = (size_t)n * ldk; a.ldk = ldk; a.V = bb.V; a.W = bb.W; a.n = n; a.r0 = r0;
+  int rc;
+  if ((rc = profile_mark_begin(PROF_SYR2K, st))) return rc;
+  if (G == 1) {
+    const int ntile = (m + 63) / 64;
+    const dim3 grid((ntile + 7) / 8, (m + S3_BM - 1) / S3_BM, T);
+    syr2k_row_kernel<64, 8, 1><<<grid, 256, syr2k_smem<64, 1>(), st>>>(a);
+  } else {
+    const int ntile = (m + 31) / 32;
+    const dim3 grid((ntile + 15) / 16, (m + S3_BM - 1) / S3_BM, T);
+    syr2k_row_kernel<32, 16, 2><<<grid, 256, syr2k_smem<32, 2>(), st>>>(a);
+  }
+  CHD_LAUNCHED();
+  if ((rc = profile_mark_end(PROF_SYR2K, st))) return rc;
   return CHD_OK;
 }
 
@@ -1339,18 +1453,24 @@ int band_device_init(Plan* pl) {
                                 (int)(SY_NST * SymmCfg<32>::STAGE * sizeof(double))));
   CHD_CUDA(cudaFuncSetAttribute(symm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(SY_NST * SymmCfg<64>::STAGE * sizeof(double))));
-  CHD_CUDA(cudaFuncSetAttribute(syr2k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((S2_BM + S2_BN) * S2_S * sizeof(double))));
   CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
-  CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((S3_BM + 2 * 32) * S2_S * sizeof(double))));
-  CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((S3_BM + 2 * 64) * S2_S * sizeof(double))));
+  CHD_CUDA(cudaFuncSetAttribute(zupdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZU_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)syr2k_smem<64, 1>()));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<32, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)syr2k_smem<32, 2>()));
   CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
   CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   CHD_CUDA(cudaFuncSetAttribute(backtransform2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)pl->smem_optin));
+  // panels per deferred-update group (CHD_KD=1: trailing update after every panel)
+  pl->band_kd = KD;
+  if (const char* e = getenv("CHD_KD")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= KD) pl->band_kd = v;
+  }
   // largest cluster the register-resident panel QR may use: 16 (non-portable) when the device can co-schedule it
   const char* e = getenv("CHD_QR_REG");     // tuning / test switch: 0 disables the register-resident kernel
   if (e && atoi(e) == 0) {
@@ -1377,54 +1497,67 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
   const int n = pl->n;
   if (nz > SY_ZW || (ldk & 1)) return CHD_EINVAL;
   const int reg_max_cs = pl->qr_reg_max_cs;
+  const int kd = pl->band_kd;
   const size_t strideA = (size_t)n * ldk;
   if (ldk > n) {
     zero_pad_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(K, strideA, ldk, n);
     CHD_LAUNCHED();
   }
-  {
-    Refl0Args a;
-    a.ga = ga; a.V = bb.V; a.v0 = bb.v0; a.Tf = bb.Tf; a.tf_stride = bb.tf_stride; a.tau0 = bb.tau0;
-    a.beta0 = beta0; a.n = n;
-    refl0_kernel<<<T, 256, 0, st>>>(a);
-    CHD_LAUNCHED();
-  }
-  int rc;
-  if ((rc = trailing_launch(pl, K, ldk, T, B, ldb, nz, 0, 0, bb, st))) return rc;
   const int np = band_npanels(n);
-  for (int p = 1; p <= np; ++p) {
+  int rc;
+  // slots: 0 = H_{-1} (r0 = 0), p >= 1 = QR panel p (columns c0 = (p-1) NB .., rows r0 = p NB ..); groups of kd
+  // consecutive slots share one trailing update
+  for (int p = 0; p <= np; ++p) {
+    const int q = p % kd;
     const int r0 = p * NB, c0 = r0 - NB, m = n - r0;
-    QrArgs a;
-    a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V; a.Tf = bb.Tf + (size_t)p * NB * NB;
-    a.tf_stride = bb.tf_stride; a.n = n; a.r0 = r0; a.c0 = c0;
-    size_t smem;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.stream = st;
-    if ((rc = profile_mark_begin(PROF_QR, st))) return rc;
-    int rcs = 1;
-    while (rcs < reg_max_cs && (m + rcs - 1) / rcs > RG_THREADS) rcs *= 2;
-    if (reg_max_cs > 0 && (m + rcs - 1) / rcs <= RG_THREADS) {
-      a.RP = (m + rcs - 1) / rcs; a.RS = 0;
-      cfg.gridDim = dim3(rcs, T);
-      cfg.blockDim = dim3(RG_THREADS);
-      cfg.dynamicSmemBytes = 0;
-      at[0].val.clusterDim.x = rcs;
-      CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_reg_kernel, a));
+    if (p == 0) {
+      Refl0Args a;
+      a.ga = ga; a.V = bb.V; a.v0 = bb.v0; a.Tf = bb.Tf; a.tf_stride = bb.tf_stride; a.tau0 = bb.tau0;
+      a.beta0 = beta0; a.n = n;
+      refl0_kernel<<<T, 256, 0, st>>>(a);
+      CHD_LAUNCHED();
     } else {
-      const int cs = qr_cluster_size(pl, m, a.RP, a.RS, smem);
-      cfg.gridDim = dim3(cs, T);
-      cfg.blockDim = dim3(QR_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      at[0].val.clusterDim.x = cs;
-      CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_kernel, a));
+      if ((rc = profile_mark_begin(PROF_QR, st))) return rc;
+      if (q > 0) {
+        // bring this panel's block column up to date with the pending reflectors of its group
+        PupdArgs u;
+        u.A = K; u.strideA = strideA; u.ldk = ldk; u.Va = bb.V; u.Wa = bb.W; u.n = n; u.c0 = c0;
+        panel_update_kernel<<<dim3((n - c0 + PU_BM - 1) / PU_BM, T), 256, PU_SMEM, st>>>(u);
+        CHD_LAUNCHED();
+      }
+      QrArgs a;
+      a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = bb.V + q * NB; a.Tf = bb.Tf + (size_t)p * NB * NB;
+      a.tf_stride = bb.tf_stride; a.n = n; a.r0 = r0; a.c0 = c0;
+      size_t smem;
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cfg.stream = st;
+      int rcs = 1;
+      while (rcs < reg_max_cs && (m + rcs - 1) / rcs > RG_THREADS) rcs *= 2;
+      if (reg_max_cs > 0 && (m + rcs - 1) / rcs <= RG_THREADS) {
+        a.RP = (m + rcs - 1) / rcs; a.RS = 0;
+        cfg.gridDim = dim3(rcs, T);
+        cfg.blockDim = dim3(RG_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        at[0].val.clusterDim.x = rcs;
+        CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_reg_kernel, a));
+      } else {
+        const int cs = qr_cluster_size(pl, m, a.RP, a.RS, smem);
+        cfg.gridDim = dim3(cs, T);
+        cfg.blockDim = dim3(QR_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        at[0].val.clusterDim.x = cs;
+        CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_kernel, a));
+      }
+      g_launches.fetch_add(1);
+      if ((rc = profile_mark_end(PROF_QR, st))) return rc;
     }
-    g_launches.fetch_add(1);
-    if ((rc = profile_mark_end(PROF_QR, st))) return rc;
-    if ((rc = trailing_launch(pl, K, ldk, T, B, ldb, nz, r0, p, bb, st))) return rc;
+    if ((rc = slot_launch(pl, K, ldk, T, B, ldb, nz, r0, p, q, bb, st))) return rc;
+    if (q == kd - 1 || p == np)
+      if ((rc = group_update_launch(pl, K, ldk, T, r0, q + 1, bb, st))) return rc;
   }
   band_extract_kernel<<<dim3(min((n * CHD_CHASE_LD + 255) / 256, 1024), T), 256, 0, st>>>(K, strideA, ldk, n,
                                                                                              bb.bandS, bb.bandW);

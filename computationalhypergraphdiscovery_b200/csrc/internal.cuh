@@ -23,7 +23,7 @@ int gamma_launch(const Plan* pl, const double* d, const double* e, const double*
                  int T, cudaStream_t st, double* gu_out = nullptr);
 // ---- two-stage reduction (band.cu, chase.cu, bandsolve.cu)
 struct BandBuffers {
-  double *V, *Y, *W, *Tf, *Mpart, *Zpart, *Mred, *Zred, *v0, *tau0, *bandS, *bandW;
+  double *V, *Y, *W, *Tf, *Mpart, *Zpart, *Gpart, *Mred, *Zred, *Gred, *TM, *TZ, *v0, *tau0, *bandS, *bandW;
   size_t tf_stride;
 };
 int band_npanels(int n);

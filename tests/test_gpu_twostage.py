@@ -187,3 +187,36 @@ def test_regress_two_stage_matches_oracle(n, N):
             ybd = r["yb"][t].cpu().numpy()
             assert np.linalg.norm(ybd - yb) <= 1e-7 * np.linalg.norm(yb), (spec, t)
             assert abs(got["lambda_min"] - info["eigenvalues"][0]) < 1e-11 * abs(info["eigenvalues"][-1])
+
+
+@pytest.mark.parametrize("n", [70, 333, 1100])
+def test_deferred_group_update_equals_per_panel_update(n, monkeypatch):
+    """The grouped trailing update (KD = 2, default) and the per-panel update (CHD_KD=1) are the same orthogonal
+    reduction: band form, Q^T S, reflectors and beta0 agree to rounding on a well-conditioned matrix."""
+    nat = _native()
+    rng = np.random.default_rng(9)
+    F = rng.standard_normal((n, n))
+    K = F @ F.T / n + np.eye(n)
+    ga = rng.standard_normal(n)
+    S = rng.standard_normal((1, n, 100))
+    res = []
+    for kd in ("1", "2"):
+        monkeypatch.setenv("CHD_KD", kd)
+        plan = nat.Plan(n, 6, 6)
+        dev = plan.device
+        Kd = torch.zeros((1, n, plan.ldk), dtype=torch.float64, device=dev)
+        Kd[0, :, :n] = torch.from_numpy(K).to(dev)
+        Bd = torch.from_numpy(S).to(dev).contiguous()
+        band, b0 = plan.band_reduce(Kd, torch.from_numpy(ga[None, :]).to(dev).contiguous(), Bd)
+        torch.cuda.synchronize()
+        res.append((band.cpu().numpy()[0, :, :nat.BAND + 1], b0.cpu().numpy(), Bd.cpu().numpy(),
+                    np.tril(Kd.cpu().numpy()[0, :, :n], -(nat.BAND + 1))))
+    (b1, beta1, B1, V1), (b2, beta2, B2, V2) = res
+    model = ts.stage1_deferred(K, ga, nat.BAND, S[0], 2)
+    scale = np.abs(K).max()
+    assert np.abs(b1 - b2).max() <= 1e-12 * scale * n
+    assert np.abs(b2 - model["band"]).max() <= 1e-12 * scale * n
+    assert abs(beta1[0] - beta2[0]) <= 1e-14 * abs(beta1[0])
+    assert np.abs(B1 - B2).max() <= 1e-11 * np.abs(S).max() * np.sqrt(n)
+    assert np.abs(B2[0] - model["Bq"]).max() <= 1e-11 * np.abs(S).max() * np.sqrt(n)
+    assert np.abs(V1 - V2).max() <= 1e-10           # reflectors stored below the band

@@ -127,3 +127,24 @@ def test_chase_pipeline_rule_is_sufficient(n, b, seed):
     d_par, e_par = ts.ChaseTasks(band).run(rng)
     np.testing.assert_allclose(d_par, d_seq, rtol=0, atol=1e-11 * np.abs(d_seq).max())
     np.testing.assert_allclose(np.abs(e_par), np.abs(e_seq), rtol=0, atol=1e-11 * np.abs(d_seq).max())
+
+
+@pytest.mark.parametrize("n,b", [(70, 8), (64, 8), (37, 4), (9, 4), (131, 32), (200, 32)])
+@pytest.mark.parametrize("kd", [1, 2, 3])
+def test_deferred_trailing_update_equals_per_panel_update(n, b, kd):
+    """The grouped (deferred) trailing update of csrc/band.cu -- stale matrix + thin block-column update + Y / M
+    corrections + one rank-2*kd*b update per group -- gives the same band form, reflectors and Q^T S as the
+    per-panel update."""
+    rng = np.random.default_rng(n + b)
+    Xr = rng.standard_normal((n, n))
+    K = Xr @ Xr.T / n + np.eye(n)
+    ga = rng.standard_normal(n)
+    S = rng.standard_normal((n, 5))
+    r1 = ts.stage1(K, ga, b, S)
+    r2 = ts.stage1_deferred(K, ga, b, S, kd)
+    scale = np.abs(r1["band"]).max()
+    assert np.abs(r1["band"] - r2["band"]).max() <= 1e-12 * scale
+    assert np.abs(r1["Bq"] - r2["Bq"]).max() <= 1e-11 * np.abs(S).max()
+    assert len(r1["panels"]) == len(r2["panels"])
+    for (ra, Va, Ta), (rb, Vb, Tb) in zip(r1["panels"], r2["panels"]):
+        assert ra == rb and np.abs(Va - Vb).max() <= 1e-10 and np.abs(Ta - Tb).max() <= 1e-10

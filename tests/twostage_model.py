@@ -91,6 +91,74 @@ def stage1(K, ga, b, S=None):
     return dict(band=band, beta0=beta0, panels=panels, v0=v0, tau0=tau0, Bq=Bq, resid=resid)
 
 
+def stage1_deferred(K, ga, b, S=None, kd=2):
+    """stage1 with the trailing update DEFERRED over groups of `kd` consecutive panels, the way csrc/band.cu runs it:
+    slot 0 is H_{-1} (a block reflector with one non-zero column), slots 1.. are the QR panels; slots (0,1), (2,3), ...
+    form groups.  Inside a group the trailing matrix stays STALE: the next panel's block column is brought up to date
+    by a thin update, its Y = A22 V is computed from the stale matrix plus the corrections
+        Y <- Y_stale - V_a (W_a^T V) - W_a (V_a^T V),    M = V^T Y = M_stale - G2^T G1 - G1^T G2,
+    and ONE rank-2*kd*b update  A22 -= sum_q V_q W_q^T + W_q V_q^T  closes the group (twice the arithmetic intensity
+    of the per-panel update for kd = 2).  Only the lower triangle is referenced, like the kernels do."""
+    n = K.shape[0]
+    A = np.tril(K.copy())
+    Bq = None if S is None else S.copy()
+    v0, tau0, beta0 = reflector(ga.copy())
+
+    def symm_lower(r0, V):            # Y = A22 V from the lower triangle of A[r0:, r0:]
+        L = A[r0:, r0:]
+        return L @ V + np.tril(L, -1).T @ V
+
+    panels = []
+    slots = []                        # (r0, V (n - r0 x b), T (b x b))
+    V0 = np.zeros((n, b))
+    V0[:, 0] = v0
+    T0 = np.zeros((b, b))
+    T0[0, 0] = tau0
+    slots.append((0, V0, T0))
+    pend = []                         # pending (r0, V, W) of the current group, rows indexed from their own r0
+    k = 0
+    while True:
+        if slots:
+            r0, V, T = slots.pop()
+        else:
+            c0 = k * b
+            r0 = c0 + b
+            if n - r0 < 2:
+                break
+            # thin update of this panel's block column [c0:, c0:r0] with the pending reflectors of the group
+            for (ra, Va, Wa) in pend:
+                o = c0 - ra
+                blk = Va[o:] @ Wa[o:o + b].T + Wa[o:] @ Va[o:o + b].T
+                A[c0:, c0:r0] -= blk
+            A[c0:r0, c0:r0] = np.tril(A[c0:r0, c0:r0])
+            R, V, tau, T = panel_qr(A[r0:, c0:r0])
+            A[r0:, c0:r0] = R
+            panels.append((r0, V, T))
+            k += 1
+        Y = symm_lower(r0, V)
+        M = V.T @ Y
+        for (ra, Va, Wa) in pend:     # corrections for the stale trailing matrix
+            o = r0 - ra
+            G1 = Wa[o:].T @ V
+            G2 = Va[o:].T @ V
+            Y -= Va[o:] @ G1 + Wa[o:] @ G2
+            M -= G2.T @ G1 + G1.T @ G2
+        W = (Y - 0.5 * V @ (T.T @ M)) @ T
+        if Bq is not None:
+            Bq[r0:] -= V @ (T.T @ (V.T @ Bq[r0:]))
+        pend.append((r0, V, W))
+        next_exists = n - ((k + 1) * b) >= 2
+        if len(pend) == kd or not next_exists:
+            for (ra, Va, Wa) in pend:
+                o = r0 - ra
+                A[r0:, r0:] -= np.tril(Va[o:] @ Wa[o:].T + Wa[o:] @ Va[o:].T)
+            pend = []
+    band = np.zeros((n, b + 1))
+    for t in range(min(b + 1, n)):
+        band[t:, t] = np.diagonal(A, -t)
+    return dict(band=band, beta0=beta0, panels=panels, v0=v0, tau0=tau0, Bq=Bq)
+
+
 def apply_Q(s1, x):
     """Q x with Q = H_{-1} Q_0 Q_1 ... (the back-transformation yb = -beta0 Q x_b)."""
     x = np.array(x, dtype=np.float64, copy=True)
