@@ -32,10 +32,16 @@ for rep in range(2):
     K = plan.gram(desc, Xd, w)
     gmin = torch.full((T,), 1e-9, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    if rep == 1 and os.environ.get("CHD_PROF_CATS"):
+        nat.profile_enable(True)
     e0.record()
     r = plan.regress(K, ga, keys, gmin, mode=1)
     e1.record()
     torch.cuda.synchronize()
+    if rep == 1 and os.environ.get("CHD_PROF_CATS"):
+        cats = nat.profile_read_all()
+        nat.profile_enable(False)
+        print("   per matrix (ms): " + ", ".join(f"{k} {v[0] / T:.2f}" for k, v in cats.items()), flush=True)
     print(f"rep {rep}: regress n={n} T={T} {kind}: {e0.elapsed_time(e1):.1f} ms, {e0.elapsed_time(e1) / T:.2f} ms/matrix, "
           f"noise[0]={r['noise'][0].item():.12g} gamma[0]={r['gamma'][0].item():.8g}", flush=True)
     del K
