@@ -230,6 +230,7 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
     CHD_CUDA(cudaGetDevice(&cur));
     if (cur != device) CHD_CUDA(cudaSetDevice(device));
     int rc = band_device_init(pl);
+    if (!rc) rc = band_tma_device_init(pl);
     if (!rc) rc = chase_device_init(pl);
     if (!rc) rc = tridiag_device_init(pl);
     if (!rc) rc = act_device_init(pl);

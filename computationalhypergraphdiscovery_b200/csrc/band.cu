@@ -1434,6 +1434,10 @@ static int group_update_launch(const Plan* pl, double* K, int ldk, int T, int r0
   a.A = K; a.strideA = (size_t)n * ldk; a.ldk = ldk; a.V = bb.V; a.W = bb.W; a.n = n; a.r0 = r0;
   int rc;
   if ((rc = profile_mark_begin(PROF_SYR2K, st))) return rc;
+  if (pl->syr2k_tma) {
+    if ((rc = syr2k_tma_launch(pl, K, ldk, T, r0, G, bb.V, bb.W, st))) return rc;
+    return profile_mark_end(PROF_SYR2K, st);
+  }
   if (G == 1) {
     const int ntile = (m + 63) / 64;
     const dim3 grid((ntile + 7) / 8, (m + S3_BM - 1) / S3_BM, T);

@@ -1,0 +1,217 @@
+// Trailing update of the dense -> band stage as a TMA-fed, warp-specialised DMMA kernel (sm_100a):
+//     A22 -= Z Z'^T,   Z = [V_a V_b | W_a W_b],  Z' = [W_a W_b | V_a V_b]     (K = 128 for a group of two panels)
+// replaces, together with the rest of band.cu, the O(n^3) part of jnp.linalg.eigh (interpolatory.py:48).
+//
+//   * one CTA = 1 producer warp + 8 DMMA consumer warps; it owns a 128-row block I and walks a chunk of 16-column
+//     tiles J of that block row (lower triangle only);
+//   * every tile of A, of Z_I (once per CTA) and of Z'_J (once per tile) travels global -> shared memory as
+//     16-column boxes through tensor maps (cp.async.bulk.tensor, SASS UTMALDG) with the 128-byte swizzle, which makes
+//     every DMMA fragment load bank-conflict free without padding;
+//   * a 3-stage ring of {A tile, Z'_J tile} is handed from the producer to the consumers through mbarrier full / empty
+//     pairs (SASS SYNCS): the consumers never meet at a CTA-wide barrier, the producer runs up to three tiles ahead,
+//     so the HBM stream (A read + write) and the DMMA pipe overlap instead of alternating;
+//   * accumulators start at -A (read from the staged tile), results go from registers to global memory.
+// FP64 has no tcgen05 kind: DMMA m8n8k4 (mma.sync) is the FP64 tensor instruction of sm_100a.
+#include "internal.cuh"
+#include "tma.cuh"
+
+namespace chd {
+
+namespace {
+
+constexpr int NB = CHD_BAND;
+constexpr int LDV = 2 * NB;          // row stride of the V / W operand arrays (band.cu: two panels side by side)
+constexpr int TM_BM = 128;           // rows of the CTA's block
+constexpr int TM_BN = 16;            // tile columns (one 16-column box)
+constexpr int TM_NST = 3;            // ring depth
+constexpr int TM_CONS_WARPS = 8;
+constexpr int TM_THREADS = 32 * (1 + TM_CONS_WARPS);
+constexpr int TM_CH = 32;            // tiles per CTA (512 columns)
+constexpr int BOX_ROWS = 16;         // every box is 16 columns x 16 rows (2 KB)
+constexpr int BOX_BYTES = 16 * BOX_ROWS * 8;
+
+// shared memory (bytes): Z_I: KB boxes-columns of 128 rows; per stage: Z'_J (KB box-columns of 16 rows) + A tile
+template <int G> struct TmCfg {
+  static constexpr int KT = 2 * G * NB;                 // K of the update (64 or 128)
+  static constexpr int KB = KT / 16;                    // 16-column boxes along K
+  static constexpr int ZI_BYTES = KB * TM_BM * 128;     // 64 / 128 KB
+  static constexpr int ZJ_BYTES = KB * TM_BN * 128;     // 8 / 16 KB
+  static constexpr int A_BYTES = TM_BM * 128;           // 16 KB
+  static constexpr int STAGE_BYTES = ZJ_BYTES + A_BYTES;
+  static constexpr int BAR_OFF = ZI_BYTES + TM_NST * STAGE_BYTES;
+  static constexpr int SMEM = BAR_OFF + 64 + 1024;      // + barriers + slack for the 1024-byte alignment
+};
+
+struct TmArgs {
+  double* A; size_t strideA; int ldk;
+  int n, r0;
+};
+
+template <int G>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapV,
+                 const __grid_constant__ CUtensorMap mapW, TmArgs a) {
+  using C = TmCfg<G>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment (swizzle period) by pointer arithmetic on the shared array, so that the compiler keeps the
+  // shared address space (LDS, not generic LD)
+  uint8_t* sm = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* zi = sm;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);
+  uint64_t* full = bars;                 // TM_NST
+  uint64_t* empty = bars + TM_NST;       // TM_NST
+  uint64_t* zi_full = bars + 2 * TM_NST;
+
+  const int t = blockIdx.z;
+  const int n = a.n, r0 = a.r0;
+  const int i0 = r0 + TM_BM * blockIdx.y;
+  // 16-column tiles of this block row that touch the lower triangle: j0 = r0 + 16 jt <= i0 + 127, j0 < n
+  const int njt = min((i0 + TM_BM - r0) / TM_BN, (n - r0 + TM_BN - 1) / TM_BN);
+  const int jt_lo = TM_CH * blockIdx.x, jt_hi = min(njt, jt_lo + TM_CH);
+  if (jt_lo >= jt_hi) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < TM_NST; ++s) {
+      tma::mbar_init(full + s, 1);
+      tma::mbar_init(empty + s, TM_CONS_WARPS);
+    }
+    tma::mbar_init(zi_full, 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (wid == 0) {
+    // ===================== producer warp: all global -> shared traffic =====================
+    if (lane == 0) {
+      tma::prefetch_map(&mapA);
+      tma::prefetch_map(&mapV);
+      tma::prefetch_map(&mapW);
+      tma::mbar_expect_tx(zi_full, C::ZI_BYTES);
+    }
+    __syncwarp();
+    // Z_I = [V_I | W_I]: box-column kb (16 K-columns) x 8 row boxes; lanes share the copies
+    for (int b = lane; b < C::KB * (TM_BM / BOX_ROWS); b += 32) {
+      const int kb = b / (TM_BM / BOX_ROWS), rb = b % (TM_BM / BOX_ROWS);
+      const bool fromV = kb < C::KB / 2;
+      const int col = 16 * (fromV ? kb : kb - C::KB / 2);
+      tma::load_box(zi + kb * (TM_BM * 128) + rb * BOX_BYTES, fromV ? &mapV : &mapW, col, i0 + BOX_ROWS * rb, t,
+                    zi_full);
+    }
+    for (int jt = jt_lo; jt < jt_hi; ++jt) {
+      const int it = jt - jt_lo, s = it % TM_NST, use = it / TM_NST;
+      if (use > 0) tma::mbar_wait(empty + s, (use - 1) & 1);      // consumers have drained the previous use
+      uint8_t* st = sm + C::ZI_BYTES + s * C::STAGE_BYTES;
+      const int j0 = r0 + TM_BN * jt;
+      if (lane == 0) tma::mbar_expect_tx(full + s, C::STAGE_BYTES);
+      __syncwarp();
+      // Z'_J = [W_J | V_J]: KB boxes of 16 rows; the A tile: 8 boxes of 16 rows
+      for (int b = lane; b < C::KB + TM_BM / BOX_ROWS; b += 32) {
+        if (b < C::KB) {
+          const bool fromW = b < C::KB / 2;
+          const int col = 16 * (fromW ? b : b - C::KB / 2);
+          tma::load_box(st + b * BOX_BYTES, fromW ? &mapW : &mapV, col, j0, t, full + s);
+        } else {
+          const int rb = b - C::KB;
+          tma::load_box(st + C::ZJ_BYTES + rb * BOX_BYTES, &mapA, j0, i0 + BOX_ROWS * rb, t, full + s);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumer warps: DMMA =====================
+  const int cw = wid - 1;                    // rows 16 cw .. 16 cw + 15 of the block, all 16 tile columns
+  const int fr = lane >> 2, fk = lane & 3;
+  // swizzled byte offsets of this lane's fragment element inside a 128-byte row: column kk + fk of a 16-column box,
+  // kk = 0, 4, 8, 12  (chunk = ((kk + fk) / 2) ^ fr, see tma::swz128; rows used here are = fr mod 8)
+  uint32_t foff[4];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) foff[c4] = tma::swz128(fr, 4 * c4 + fk);
+  const uint8_t* zi_row = zi + (16 * cw) * 128;               // foff carries the lane's row fr; + 8 x rows: + 1024
+  double* Ag = a.A + (size_t)t * a.strideA;
+  tma::mbar_wait(zi_full, 0);
+  for (int jt = jt_lo; jt < jt_hi; ++jt) {
+    const int it = jt - jt_lo, s = it % TM_NST, use = it / TM_NST;
+    const uint8_t* st = sm + C::ZI_BYTES + s * C::STAGE_BYTES;
+    const uint8_t* zj_row = st;                               // foff carries the lane's row fr; + 8 y rows: + 1024
+    const uint8_t* at = st + C::ZJ_BYTES;
+    tma::mbar_wait(full + s, use & 1);
+    // accumulators start at -A: c0, c1 = columns 8 y + 2 fk, + 1 of row 16 cw + 8 x + fr
+    double acc[2][2][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const double2 o = *reinterpret_cast<const double2*>(at + tma::swz128(16 * cw + 8 * x + fr, 8 * y + 2 * fk));
+        acc[x][y][0] = -o.x;
+        acc[x][y][1] = -o.y;
+      }
+#pragma unroll
+    for (int kb = 0; kb < C::KB; ++kb) {
+      const uint8_t* zik = zi_row + kb * (TM_BM * 128);
+      const uint8_t* zjk = zj_row + kb * BOX_BYTES;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        double af[2], bf[2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) af[x] = *reinterpret_cast<const double*>(zik + x * 1024 + foff[c4]);
+#pragma unroll
+        for (int y = 0; y < 2; ++y) bf[y] = *reinterpret_cast<const double*>(zjk + y * 1024 + foff[c4]);
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+          for (int y = 0; y < 2; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+      }
+    }
+    // this warp is done with the stage: hand it back to the producer before the (slow) global stores
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty + s);
+    const int j0 = r0 + TM_BN * jt;
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int i = i0 + 16 * cw + 8 * x + fr;
+      if (i < n) {
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          const int j = j0 + 8 * y + 2 * fk;
+          double* p = Ag + (size_t)i * a.ldk + j;
+          if (j + 1 <= i) *reinterpret_cast<double2*>(p) = make_double2(-acc[x][y][0], -acc[x][y][1]);
+          else if (j <= i) p[0] = -acc[x][y][0];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int band_tma_device_init(Plan* pl) {
+  pl->syr2k_tma = 1;
+  if (const char* e = getenv("CHD_SYR2K_TMA")) pl->syr2k_tma = atoi(e) ? 1 : 0;
+  if (!tma::encode_fn()) pl->syr2k_tma = 0;
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<1>::SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<2>::SMEM));
+  return CHD_OK;
+}
+
+// A[r0:, r0:] -= sum over the G panels of the group (V, W: T x n x LDV, column blocks 0 .. G-1), lower tiles only
+int syr2k_tma_launch(const Plan* pl, double* K, int ldk, int T, int r0, int G, const double* V, const double* W,
+                     cudaStream_t st) {
+  const int n = pl->n, m = n - r0;
+  CUtensorMap mapA, mapV, mapW;
+  int rc;
+  if ((rc = tma::make_map_f64(&mapA, K, (uint64_t)n, (uint64_t)n, (uint64_t)T, (uint64_t)ldk, BOX_ROWS))) return rc;
+  if ((rc = tma::make_map_f64(&mapV, V, (uint64_t)LDV, (uint64_t)n, (uint64_t)T, (uint64_t)LDV, BOX_ROWS))) return rc;
+  if ((rc = tma::make_map_f64(&mapW, W, (uint64_t)LDV, (uint64_t)n, (uint64_t)T, (uint64_t)LDV, BOX_ROWS))) return rc;
+  TmArgs a;
+  a.A = K; a.strideA = (size_t)n * ldk; a.ldk = ldk; a.n = n; a.r0 = r0;
+  const int ntile = (m + TM_BN - 1) / TM_BN;
+  const dim3 grid((ntile + TM_CH - 1) / TM_CH, (m + TM_BM - 1) / TM_BM, T);
+  if (G == 1) syr2k_tma_kernel<1><<<grid, TM_THREADS, TmCfg<1>::SMEM, st>>>(mapA, mapV, mapW, a);
+  else syr2k_tma_kernel<2><<<grid, TM_THREADS, TmCfg<2>::SMEM, st>>>(mapA, mapV, mapW, a);
+  CHD_LAUNCHED();
+  return CHD_OK;
+}
+
+}  // namespace chd

@@ -45,6 +45,7 @@ struct Plan {
   int chase_ctas_per_sm;   // resident bulge-chasing CTAs per SM
   int qr_reg_max_cs;       // largest cluster of the register-resident panel QR (0: disabled)
   int band_kd;             // panels per deferred trailing update of the dense -> band stage (1 or 2)
+  int syr2k_tma;           // 1: TMA + mbarrier warp-specialised trailing update (band_tma.cu), 0: cp.async kernel
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

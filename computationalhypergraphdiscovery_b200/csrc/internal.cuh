@@ -38,6 +38,10 @@ size_t chase_prog_ints(const Plan* pl, int T);
 // per-device set-up (function attributes, occupancy queries), called by chd_plan_create on the plan's device
 int chase_device_init(Plan* pl);
 int band_device_init(Plan* pl);
+int band_tma_device_init(Plan* pl);
+// TMA-fed trailing update (band_tma.cu): A[r0:, r0:] -= sum_q V_q W_q^T + W_q V_q^T over the G panels of a group
+int syr2k_tma_launch(const Plan* pl, double* K, int ldk, int T, int r0, int G, const double* V, const double* W,
+                     cudaStream_t st);
 int tridiag_device_init(Plan* pl);
 int act_device_init(Plan* pl);
 int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e, int T, cudaStream_t st);

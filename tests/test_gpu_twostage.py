@@ -189,10 +189,13 @@ def test_regress_two_stage_matches_oracle(n, N):
             assert abs(got["lambda_min"] - info["eigenvalues"][0]) < 1e-11 * abs(info["eigenvalues"][-1])
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
 @pytest.mark.parametrize("n", [70, 333, 1100])
-def test_deferred_group_update_equals_per_panel_update(n, monkeypatch):
+def test_deferred_group_update_equals_per_panel_update(n, tma, monkeypatch):
     """The grouped trailing update (KD = 2, default) and the per-panel update (CHD_KD=1) are the same orthogonal
-    reduction: band form, Q^T S, reflectors and beta0 agree to rounding on a well-conditioned matrix."""
+    reduction: band form, Q^T S, reflectors and beta0 agree to rounding on a well-conditioned matrix -- with the
+    TMA + mbarrier trailing-update kernel (band_tma.cu, default) and with the cp.async one (CHD_SYR2K_TMA=0)."""
+    monkeypatch.setenv("CHD_SYR2K_TMA", tma)
     nat = _native()
     rng = np.random.default_rng(9)
     F = rng.standard_normal((n, n))
