@@ -143,15 +143,18 @@ __global__ void __launch_bounds__(256) quad_rows_kernel(const double* __restrict
 //   sym * yb_i yb_j P_ij (1 - 1/F_c,ij).  XT is N x n (variables major).  Members of cluster c are
 // mem_idx[mem_off[c] .. mem_off[c+1]).
 constexpr int GA_TILE = 64;
+constexpr int GA_BLOCKS = 296;  // blocks of the pair-sum kernels = per-target stride of their partial sums
 __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restrict__ XT, int n, int N, int C,
                                                           const double* __restrict__ yb,
                                                           const uint8_t* __restrict__ w,
                                                           const int32_t* __restrict__ mem_off,
                                                           const int32_t* __restrict__ mem_idx, double inv2l2,
                                                           double* __restrict__ partial, int nblk,
-                                                          const double* __restrict__ Pc, int ldk) {
+                                                          const double* __restrict__ Pc, int ldk,
+                                                          const uint8_t* __restrict__ only_flagged) {
   extern __shared__ double sacc[];  // C x 8 warps
   const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (only_flagged && !only_flagged[t]) return;   // this target is served by gauss_shared_kernel
   const int tx = tid & 15, ty = tid >> 4;
   const uint8_t* wt = w + (size_t)t * N;
   const double* y = yb + (size_t)t * n;
@@ -247,7 +250,191 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
     double s = 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) s += sacc[c * 8 + q];
-    partial[((size_t)t * nblk + blockIdx.x) * C + c] = s;
+    partial[((size_t)t * GA_BLOCKS + blockIdx.x) * C + c] = s;
+  }
+}
+
+// ---- Gaussian pair sums, SHARED across the targets of a batch.
+// The per-pair factor  R_c,ij = 1 - 1/prod_{d in c}(1 + E_d,ij)  does not depend on the target (as long as every
+// member of cluster c is active for it), only  M^t_ij = sym yb^t_i yb^t_j P^t_ij  does.  So for a batch of T targets
+//     gau[t][c] = sum_(ij) M^t_ij R_c,ij
+// is ONE GEMM (T x pairs) x (pairs x C): every exp / reciprocal is evaluated once per (pair, cluster) instead of once
+// per (pair, cluster, target), and the contraction over the pairs runs on the FP64 tensor cores (DMMA m8n8k4; the
+// R values are computed by each lane directly in its B-fragment position, M comes from shared memory).  Needs the
+// cached product maps P^t (chd_prune_chain's P_state).  Targets for which some alive cluster has only part of its
+// members active (multi-variable clusters containing the target itself or an impossible edge) are flagged and served
+// by gauss_pairs_kernel instead.
+constexpr int GS_IB = 8, GS_JB = 16;          // pair tile: 8 rows x 16 columns = 128 pairs = 32 k-steps
+constexpr int GS_TG = 32;                     // targets per group (4 DMMA row blocks)
+constexpr int GS_MP = GS_TG + 8;              // shared-memory pitch of M[pair][target] (== 8 mod 32: conflict free)
+constexpr int GS_CW = 64;                     // clusters per warp (8 DMMA column blocks), 512 per CTA pass
+constexpr size_t GS_SMEM = (size_t)2 * GS_IB * GS_JB * GS_MP * sizeof(double);
+
+// clist = clusters that are alive with at least one active member for SOME target of the batch (compact, in
+// increasing order), nc = their number; flagged[t] = 1 if some alive cluster of target t is only partly active.
+__global__ void __launch_bounds__(256) cluster_union_kernel(const uint8_t* __restrict__ w, int T, int N, int C,
+                                                            const int32_t* __restrict__ mem_off,
+                                                            const int32_t* __restrict__ mem_idx,
+                                                            int32_t* __restrict__ clist, int32_t* __restrict__ nc,
+                                                            uint8_t* __restrict__ flagged) {
+  extern __shared__ int32_t s_any[];   // C
+  const int tid = threadIdx.x;
+  for (int t = tid; t < T; t += 256) flagged[t] = 0;
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    int any = 0;
+    const int lo = mem_off[c], hi = mem_off[c + 1];
+    for (int t = 0; t < T; ++t) {
+      int act = 0;
+      for (int q = lo; q < hi; ++q) act += w[(size_t)t * N + mem_idx[q]] ? 1 : 0;
+      if (act > 0) {
+        any = 1;
+        if (act < hi - lo) flagged[t] = 1;      // benign race: every writer stores 1
+      }
+    }
+    s_any[c] = any;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int k = 0;
+    for (int c = 0; c < C; ++c)
+      if (s_any[c]) clist[k++] = c;
+    *nc = k;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __restrict__ X, int n, int N, int C, int T,
+                                                              const double* __restrict__ yb,
+                                                              const int32_t* __restrict__ mem_off,
+                                                              const int32_t* __restrict__ mem_idx,
+                                                              const int32_t* __restrict__ clist,
+                                                              const int32_t* __restrict__ ncp, double inv2l2,
+                                                              double* __restrict__ partial, int nblk,
+                                                              const double* __restrict__ Pc, int ldk) {
+  __shared__ double etab[64];
+  extern __shared__ __align__(16) double gs_smem[];
+  constexpr int MS_SZ = GS_IB * GS_JB * GS_MP;                    // M[pair][target], double buffered
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int tg0 = blockIdx.y * GS_TG;                // first target of this group
+  const int nc = *ncp;
+  exp_table_load(etab);
+  const int ib_n = (n + GS_IB - 1) / GS_IB, jb_n = (n + GS_JB - 1) / GS_JB;
+  // producer geometry for M: thread -> (target tp, row ip), 16 columns
+  const int tp = tid >> 3, ip = tid & 7;
+  const bool tp_ok = tg0 + tp < T;
+  const double* yt = yb + (size_t)(tp_ok ? tg0 + tp : 0) * n;
+  const double* Pt = Pc + (size_t)(tp_ok ? tg0 + tp : 0) * n * ldk;
+  // tiles of the lower triangle (block row bi of 8 rows: column blocks 0 .. (8 bi + 7) / 16), dealt round robin
+  auto fill = [&](int bi, int bj, double* dst) {
+    const int i = bi * GS_IB + ip, j0 = bj * GS_JB;
+    double pv[GS_JB];
+    const bool row_ok = tp_ok && i < n;
+    const double yi = row_ok ? yt[i] : 0.0;
+#pragma unroll
+    for (int b = 0; b < GS_JB; b += 2) {
+      double2 v = make_double2(0.0, 0.0);
+      if (row_ok && j0 + b <= i) {
+        if (j0 + b + 1 < ldk) v = *reinterpret_cast<const double2*>(Pt + (size_t)i * ldk + j0 + b);
+        else v.x = Pt[(size_t)i * ldk + j0 + b];
+      }
+      pv[b] = v.x; pv[b + 1] = v.y;
+    }
+#pragma unroll
+    for (int b = 0; b < GS_JB; ++b) {
+      const int j = j0 + b;
+      double m = 0.0;
+      if (row_ok && j <= i) m = ((j == i) ? 1.0 : 2.0) * yi * yt[j] * pv[b];
+      dst[(ip * GS_JB + b) * GS_MP + tp] = m;
+    }
+  };
+  for (int cpass = 0; cpass * (8 * GS_CW) < nc; ++cpass) {
+    const int cb = cpass * (8 * GS_CW) + wid * GS_CW;   // first compact cluster index of this warp
+    // this lane's B-fragment clusters: compact index cb + 8 nb + fr
+    int cl_lo[8], cl_hi[8];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int k = cb + 8 * nb + fr;
+      if (k < nc) { const int c = clist[k]; cl_lo[nb] = mem_off[c]; cl_hi[nb] = mem_off[c + 1]; }
+      else { cl_lo[nb] = 0; cl_hi[nb] = 0; }
+    }
+    double acc[4][8][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+    // walk this CTA's tiles
+    long long tile = blockIdx.x;
+    int bi = 0;
+    long long row_start = 0;          // index of the first tile of block row bi
+    auto locate = [&](long long tl) {   // advance (bi, row_start) to the block row holding tile tl
+      while (bi < ib_n) {
+        const long long cnt = min((long long)jb_n, (long long)((bi * GS_IB + GS_IB - 1) / GS_JB + 1));
+        if (tl < row_start + cnt) return true;
+        row_start += cnt;
+        ++bi;
+      }
+      return false;
+    };
+    int buf = 0;
+    bool have = locate(tile);
+    if (have) fill(bi, (int)(tile - row_start), gs_smem);
+    __syncthreads();
+    while (have) {
+      const int cbi = bi, cbj = (int)(tile - row_start);
+      // prefetch the next tile's M into the other buffer
+      const long long ntile = tile + nblk;
+      const bool nhave = locate(ntile);
+      if (nhave) fill(bi, (int)(ntile - row_start), gs_smem + (buf ^ 1) * MS_SZ);
+      const double* M = gs_smem + buf * MS_SZ;
+      const int i0 = cbi * GS_IB, j0 = cbj * GS_JB;
+      if (cb < nc) {
+#pragma unroll 1
+        for (int q = 0; q < GS_IB * GS_JB / 4; ++q) {
+          const int il = q >> 2, jl = 4 * (q & 3) + fk;
+          const int i = min(i0 + il, n - 1), j = min(j0 + jl, n - 1);
+          const double* xi = X + (size_t)i * N;
+          const double* xj = X + (size_t)j * N;
+          double bf[8];
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) {
+            double F = 1.0;
+            for (int m = cl_lo[nb]; m < cl_hi[nb]; ++m) {
+              const int d = mem_idx[m];
+              const double df = __ldg(xi + d) - __ldg(xj + d);
+              F *= 1.0 + exp_nonpos(-(df * df) * inv2l2, etab);
+            }
+            bf[nb] = 1.0 - rcp_ge1(F);
+          }
+          const double* mp = M + (4 * q + fk) * GS_MP + fr;
+          double af[4];
+#pragma unroll
+          for (int mb = 0; mb < 4; ++mb) af[mb] = mp[8 * mb];
+#pragma unroll
+          for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+        }
+      }
+      __syncthreads();
+      tile = ntile;
+      have = nhave;
+      buf ^= 1;
+    }
+    // partial sums of this CTA: rows = targets 8 mb + fr, columns = compact clusters cb + 8 nb + 2 fk + {0, 1}
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int t = tg0 + 8 * mb + fr;
+      if (t >= T) continue;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = cb + 8 * nb + 2 * fk + h;
+          if (k < nc) partial[((size_t)t * GA_BLOCKS + blockIdx.x) * C + clist[k]] = acc[mb][nb][h];
+        }
+    }
+    __syncthreads();
   }
 }
 
@@ -259,6 +446,7 @@ __global__ void __launch_bounds__(256) act_finalize_kernel(chd_kernel_desc kd, i
                                                            const double* __restrict__ gdot,
                                                            const double* __restrict__ rowq,
                                                            const double* __restrict__ gpart, int nblk,
+                                                           int nblk_shared, const uint8_t* __restrict__ flagged,
                                                            const double* __restrict__ energy,
                                                            uint8_t* __restrict__ alive, double* __restrict__ act,
                                                            size_t act_stride, int prune, int32_t* __restrict__ pruned,
@@ -268,6 +456,8 @@ __global__ void __launch_bounds__(256) act_finalize_kernel(chd_kernel_desc kd, i
   const int t = blockIdx.x, tid = threadIdx.x;
   const uint8_t* wt = w + (size_t)t * N;
   const double en = energy[t];
+  // Gaussian partials: from gauss_pairs_kernel (nblk blocks) or, for targets it serves, from gauss_shared_kernel
+  const int nb_t = (nblk_shared > 0 && !(flagged && flagged[t])) ? nblk_shared : nblk;
   double bv = 0.0; int bi = -1; bool bnan = false;
   for (int c = tid; c < C; c += 256) {
     double lin = 0.0, qr = 0.0;
@@ -289,7 +479,7 @@ __global__ void __launch_bounds__(256) act_finalize_kernel(chd_kernel_desc kd, i
       v = kd.scale * (2.0 * kd.alpha * lin + qr) / en;
     } else {
       double gs = 0.0;
-      for (int b = 0; b < nblk; ++b) gs += gpart[((size_t)t * nblk + b) * C + c];
+      for (int b = 0; b < nb_t; ++b) gs += gpart[((size_t)t * GA_BLOCKS + b) * C + c];
       v = (kd.quad_scale * (2.0 * kd.alpha * lin + qr) + kd.scale * gs) / en;
     }
     act[(size_t)t * act_stride + c] = v;
@@ -353,7 +543,6 @@ __global__ void members_kernel(const int32_t* __restrict__ cluster_of, int N, in
   }
 }
 
-constexpr int GA_BLOCKS = 296;  // 2 per SM
 
 size_t act_workspace(const Plan* pl, int T) {
   const size_t n = pl->n, N = pl->N, C = pl->C;
@@ -365,6 +554,7 @@ size_t act_workspace(const Plan* pl, int T) {
   b += align_up(T * N * N * sizeof(double), 256);              // Gm
   b += align_up(n * N * sizeof(double), 256);                  // XT
   b += align_up((size_t)T * GA_BLOCKS * C * sizeof(double), 256);
+  b += align_up((C + 1) * sizeof(int32_t), 256) + align_up(T, 256);   // clist + nc, flagged
   return b + 4096;
 }
 
@@ -383,6 +573,8 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
   double* Gm = cv.take<double>((size_t)T * N * N);
   double* XT = cv.take<double>((size_t)n * N);
   double* gpart = cv.take<double>((size_t)T * GA_BLOCKS * C);
+  int32_t* clist = cv.take<int32_t>(C + 1);
+  uint8_t* flagged = cv.take<uint8_t>(T);
   if (!cv.ok) {
     set_error("chd_activations: workspace too small (%zu needed, %zu given)", cv.off, ws_bytes);
     return CHD_ENOSPC;
@@ -394,7 +586,7 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
   gdot_kernel<<<dim3((N + 31) / 32, T), 256, 0, st>>>(X, n, N, yb, ga, gdot, energy);
   CHD_LAUNCHED();
   const bool quad = kd->kind != CHD_KERNEL_LINEAR;
-  int nblk = 0;
+  int nblk = 0, nblk_shared = 0;
   if (quad) {
     const int nt = (N + 31) / 32;
     gmat_kernel<<<dim3(nt, nt, T), 256, 0, st>>>(X, n, N, yb, Gm);
@@ -409,17 +601,34 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
     const int ntiles = tb * (tb + 1) / 2;
     nblk = ntiles < GA_BLOCKS ? ntiles : GA_BLOCKS;
     const size_t smem = (size_t)C * 8 * sizeof(double);
+    const bool shared = P && pl->gauss_shared;
+    if (shared) {
+      // one evaluation of every per-pair factor for the whole batch + a DMMA contraction over the pairs; the targets
+      // it cannot serve (partly active clusters) are flagged and go through gauss_pairs_kernel below
+      cluster_union_kernel<<<1, 256, (size_t)C * sizeof(int32_t), st>>>(w, T, N, C, mem_off, mem_idx, clist, clist + C,
+                                                                        flagged);
+      CHD_LAUNCHED();
+      nblk_shared = pl->sm_count < GA_BLOCKS ? pl->sm_count : GA_BLOCKS;
+      gauss_shared_kernel<<<dim3(nblk_shared, (T + GS_TG - 1) / GS_TG), 256, GS_SMEM, st>>>(
+          X, n, N, C, T, yb, mem_off, mem_idx, clist, clist + C, 1.0 / (2.0 * kd->l * kd->l), gpart, nblk_shared, P,
+          ldk);
+      CHD_LAUNCHED();
+    }
     gauss_pairs_kernel<<<dim3(nblk, T), 256, smem, st>>>(XT, n, N, C, yb, w, mem_off, mem_idx,
-                                                         1.0 / (2.0 * kd->l * kd->l), gpart, nblk, P, ldk);
+                                                         1.0 / (2.0 * kd->l * kd->l), gpart, nblk, P, ldk,
+                                                         shared ? flagged : nullptr);
     CHD_LAUNCHED();
   }
   act_finalize_kernel<<<T, 256, 0, st>>>(*kd, N, C, w, mem_off, mem_idx, gdot, quad ? rowq : nullptr, gpart, nblk,
-                                         energy, alive, act, act_stride, prune, pruned, pruned_stride);
+                                         nblk_shared, flagged, energy, alive, act, act_stride, prune, pruned,
+                                         pruned_stride);
   CHD_LAUNCHED();
   return CHD_OK;
 }
 
 int act_device_init(Plan* pl) {
+  pl->gauss_shared = getenv("CHD_GAUSS_SHARED") ? atoi(getenv("CHD_GAUSS_SHARED")) : 1;
+  CHD_CUDA(cudaFuncSetAttribute(gauss_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
   // the kernel also has static shared memory: the opt-in limit covers static + dynamic
   cudaFuncAttributes fa;
   CHD_CUDA(cudaFuncGetAttributes(&fa, gauss_pairs_kernel));

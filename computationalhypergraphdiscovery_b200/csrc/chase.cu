@@ -387,6 +387,11 @@ int chase_device_init(Plan* pl) {
     CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_cta_kernel, threads, smem));
   }
   pl->chase_ctas_per_sm = nb > 0 ? nb : 1;
+  // L2 budget for the work bands of one launch (default: everything in one launch; CHD_CHASE_L2_MB to cap) and an
+  // explicit cap on matrices per launch (CHD_CHASE_WAVE)
+  pl->chase_l2_budget = (size_t)1 << 40;
+  if (const char* e = getenv("CHD_CHASE_L2_MB")) pl->chase_l2_budget = (size_t)atoi(e) << 20;
+  pl->chase_wave = getenv("CHD_CHASE_WAVE") ? atoi(getenv("CHD_CHASE_WAVE")) : 0;
   if (const char* e = getenv("CHD_CHASE_CTAS_PER_SM")) {   // tuning: leave room for another stream's kernels
     const int v = atoi(e);
     if (v >= 1 && v < pl->chase_ctas_per_sm) pl->chase_ctas_per_sm = v;
@@ -408,18 +413,32 @@ int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e,
     // sweeps in flight per matrix: what fits on the device for all T matrices at once, at most the pipeline depth
     // n / (2 NB).  One launch: sweeps are drawn from the ticket counters, so CTAs that are not resident yet are
     // never waited for.
+    // matrices per launch: all of them, unless their work bands (n x 66 doubles each) would overflow L2 -- then the
+    // band lines thrash to DRAM between consecutive sweeps (ncu: 184 GB written for 32 matrices at n = 8192) --
+    // in which case they are chased in waves that fit
+    int wave = T;
+    {
+      const size_t band_bytes = (size_t)n * CLD * sizeof(double);
+      const size_t fit = pl->chase_l2_budget / (band_bytes ? band_bytes : 1);
+      if (fit >= 1 && (size_t)wave > fit) wave = (int)fit;
+      if (pl->chase_wave > 0 && pl->chase_wave < wave) wave = pl->chase_wave;
+    }
     const int cap = pl->sm_count * pl->chase_ctas_per_sm;        // CTAs
-    int per = cap / T;
     const int want = (n / (2 * CB) + sweeps_per_cta) / sweeps_per_cta;
-    if (per > want) per = want;
-    if (per < 1) per = 1;
-    ChaseArgs a;
-    a.bandW = bandW; a.prog = prog; a.ticket = ticket; a.err = err; a.n = n;
     int prc;
     if ((prc = profile_mark_begin(PROF_CHASE, st))) return prc;
-    if (variant == 0) chase_kernel<<<dim3(per, T), threads, smem, st>>>(a);
-    else chase_cta_kernel<<<dim3(per, T), threads, smem, st>>>(a);
-    CHD_LAUNCHED();
+    for (int t0 = 0; t0 < T; t0 += wave) {
+      const int cnt = (T - t0 < wave) ? T - t0 : wave;
+      int per = cap / cnt;
+      if (per > want) per = want;
+      if (per < 1) per = 1;
+      ChaseArgs a;
+      a.bandW = bandW + (size_t)t0 * n * CLD; a.prog = prog + (size_t)t0 * n; a.ticket = ticket + t0; a.err = err;
+      a.n = n;
+      if (variant == 0) chase_kernel<<<dim3(per, cnt), threads, smem, st>>>(a);
+      else chase_cta_kernel<<<dim3(per, cnt), threads, smem, st>>>(a);
+      CHD_LAUNCHED();
+    }
     if ((prc = profile_mark_end(PROF_CHASE, st))) return prc;
   }
   chase_extract_kernel<<<dim3((n + 255) / 256, T), 256, 0, st>>>(bandW, n, n >= 3 ? err : nullptr, d, e);

@@ -43,7 +43,10 @@ struct Plan {
   // per-device results of the *_device_init calls of chd_plan_create (function attributes are per device)
   int chase_variant;       // 1: CTA per sweep (default), 0: warp per sweep
   int chase_ctas_per_sm;   // resident bulge-chasing CTAs per SM
+  int chase_wave;          // cap on matrices per bulge-chasing launch (0: none)
+  size_t chase_l2_budget;  // bytes of work bands one bulge-chasing launch may touch
   int qr_reg_max_cs;       // largest cluster of the register-resident panel QR (0: disabled)
+  int gauss_shared;        // 1: Gaussian activations of a batch share the per-pair factors (gauss_shared_kernel)
   int band_kd;             // panels per deferred trailing update of the dense -> band stage (1 or 2)
   int syr2k_tma;           // 1: TMA + mbarrier warp-specialised trailing update (band_tma.cu), 0: cp.async kernel
 };
