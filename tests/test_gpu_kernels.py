@@ -203,3 +203,50 @@ def test_activations_match_oracle(clusters):
             assert alive_d[t, j].item() == 0
 
 
+
+
+@pytest.mark.parametrize("clusters,N,T", [(False, 40, 37), (True, 8, 8), (False, 8, 3)])
+def test_shared_gaussian_activations_match_oracle(clusters, N, T):
+    """gauss_shared_kernel (one evaluation of the per-pair factors for the whole batch + DMMA contraction; needs the
+    cached product maps, so it is reached through chd_prune_chain) against the oracle's activations
+    (helper_functions.py:113-132, kernels.py:270-278): more than one target group (T = 37 > 32), clustered variables
+    (targets inside a multi-variable cluster are flagged and served by gauss_pairs_kernel), few targets."""
+    nat = _native()
+    n = 150
+    X, names = _data(n, N, 13)
+    if clusters:
+        cl = [[names[0], names[3]], [names[1]], [names[2], names[4], names[5]], [names[6]], [names[7]]]
+    else:
+        cl = None
+    im = ochd.make_index_matrix(names, cl)
+    C = im.shape[0]
+    cluster_of = np.argmax(im, axis=0).astype(np.int32)
+    plan = nat.Plan(n, N, C)
+    dev = plan.device
+    spec = SPECS[2]
+    desc = _desc(nat, spec)
+    rng = np.random.default_rng(14)
+    w0 = np.ones((T, N), dtype=np.uint8)
+    for t in range(T):
+        w0[t, t % N] = 0
+    w0[0, (N // 2) % N] = 0                      # an impossible edge
+    alive = np.ones((T, C), dtype=np.uint8)
+    alive[1 % T, 1] = 0
+    ga = np.ascontiguousarray(X[:, np.arange(T) % N].T)
+    yb = rng.standard_normal((T, n)) * 0.1 - 0.5 * ga
+    f64 = torch.float64
+    alive_d = torch.from_numpy(alive.copy()).to(dev)
+    pc = dict(P=torch.empty((T, n, plan.ldk), dtype=f64, device=dev), valid=0)
+    out = plan.prune_chain(desc, torch.from_numpy(X).to(dev), torch.from_numpy(cluster_of).to(dev),
+                           torch.from_numpy(w0).to(dev), alive_d, torch.from_numpy(ga).to(dev),
+                           torch.from_numpy(yb.copy()).to(dev), torch.zeros((T, 2), dtype=torch.int32, device=dev),
+                           torch.zeros(T, dtype=f64, device=dev), torch.full((T,), 1e-9, dtype=f64, device=dev), 1, 1,
+                           keep_yb=False, p_cache=pc)
+    torch.cuda.synchronize()
+    act = out["act"][:, 0].cpu().numpy()
+    pruned = out["pruned"][:, 0].cpu().numpy()
+    for t in range(T):
+        am = im * w0[t][None, :] * alive[t][:, None]
+        ref = ochd.activations(spec, X, yb[t], ga[t], am, clusters)
+        np.testing.assert_allclose(act[t], ref, rtol=1e-9, atol=1e-12)
+        assert int(pruned[t]) == int(np.argmin(ref))
