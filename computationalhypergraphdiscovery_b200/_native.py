@@ -54,6 +54,7 @@ _SIGNATURES = {
     "chd_tridiag": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "chd_dmma_peak": (_i, [_i, ctypes.POINTER(_d)]),
     "chd_fp64_probe": (_i, [_i, _i, ctypes.POINTER(_d)]),
+    "chd_dmma_occupancy_probe": (_i, [_i, _i, _i, ctypes.POINTER(_d)]),
     "chd_band_workspace_bytes": (_sz, [_vp, _i]),
     "chd_band_reduce": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "chd_band_backtransform": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
@@ -347,6 +348,14 @@ def profile_read_all():
 def dmma_peak_tflops(iters=20000):
     v = ctypes.c_double()
     _check(load().chd_dmma_peak(int(iters), ctypes.byref(v)), "chd_dmma_peak")
+    return v.value
+
+
+def dmma_occupancy_probe_tflops(warps_per_sm, chains, iters=20000):
+    """DMMA rate with one CTA of `warps_per_sm` warps per SM and `chains` independent accumulators per warp."""
+    v = ctypes.c_double()
+    _check(load().chd_dmma_occupancy_probe(int(iters), int(warps_per_sm), int(chains), ctypes.byref(v)),
+           "chd_dmma_occupancy_probe")
     return v.value
 
 

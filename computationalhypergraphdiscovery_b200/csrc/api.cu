@@ -125,6 +125,25 @@ __global__ void dmma_peak_kernel(int iters, double* sink) {
   if (s == 123.456) sink[0] = s;
 }
 
+// occupancy probe: `CH` independent accumulator chains per warp (what a GEMM warp tile of CH 8x8 blocks offers)
+template <int CH>
+__global__ void dmma_chain_kernel(int iters, double* sink) {
+  double c[CH][2];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8 / CH; ++r)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
 // mode 0: DMMA only, 1: DFMA only, 2: both interleaved (8 DFMA per DMMA = equal flops): do the FP64 tensor and the
 // FP64 vector pipes add up?
 __global__ void fp64_mix_kernel(int iters, int mode, double* sink) {
@@ -495,6 +514,38 @@ extern "C" int chd_fp64_probe(int iters, int mode, double* tflops) {
   if (mode != 1) per_iter += 8.0 * 512.0;
   if (mode != 0) per_iter += 64.0 * 64.0;
   *tflops = (double)blocks * (threads / 32) * (double)iters * per_iter / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return CHD_OK;
+}
+
+extern "C" int chd_dmma_occupancy_probe(int iters, int warps_per_sm, int chains, double* tflops) {
+  if (iters <= 0 || !tflops || warps_per_sm < 1 || warps_per_sm > 32) return CHD_EINVAL;
+  int dev = 0;
+  CHD_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CHD_CUDA(cudaGetDeviceProperties(&prop, dev));
+  double* sink;
+  CHD_CUDA(cudaMalloc(&sink, 8));
+  const int blocks = prop.multiProcessorCount, threads = 32 * warps_per_sm;
+  auto launch = [&](int it) {
+    if (chains == 2) dmma_chain_kernel<2><<<blocks, threads>>>(it, sink);
+    else if (chains == 4) dmma_chain_kernel<4><<<blocks, threads>>>(it, sink);
+    else dmma_chain_kernel<8><<<blocks, threads>>>(it, sink);
+  };
+  launch(iters / 10 + 1);
+  cudaEvent_t e0, e1;
+  CHD_CUDA(cudaEventCreate(&e0));
+  CHD_CUDA(cudaEventCreate(&e1));
+  CHD_CUDA(cudaEventRecord(e0));
+  launch(iters);
+  CHD_CUDA(cudaEventRecord(e1));
+  CHD_CUDA(cudaEventSynchronize(e1));
+  g_launches.fetch_add(2);
+  float ms = 0;
+  CHD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *tflops = (double)blocks * warps_per_sm * (double)iters * 8.0 * 512.0 / (ms * 1e-3) / 1e12;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(sink);

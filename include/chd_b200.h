@@ -180,6 +180,9 @@ int chd_plan_two_stage(const chd_plan* plan);
 /* FP64 tensor-core (DMMA) throughput probe: runs `iters` back-to-back m8n8k4 chains per warp on
  * the whole GPU and returns the measured TFLOP/s (host-synchronising; used for the roofline peak). */
 int chd_dmma_peak(int iters, double* tflops);
+/* Same probe at a GEMM kernel's occupancy: one CTA of `warps_per_sm` warps per SM, `chains` (2, 4 or 8) independent
+ * accumulators per warp -- the DMMA rate a kernel with that many resident warps and that warp tile can reach at best. */
+int chd_dmma_occupancy_probe(int iters, int warps_per_sm, int chains, double* tflops);
 /* FP64 pipe probe: mode 0 = DMMA only, 1 = DFMA only, 2 = both interleaved at equal flops; returns TFLOP/s. */
 int chd_fp64_probe(int iters, int mode, double* tflops);
 
