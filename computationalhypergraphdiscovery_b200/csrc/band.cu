@@ -32,15 +32,12 @@
 
 #include <stdlib.h>
 
-#include "internal.cuh"
+#include "band.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace chd {
 
-constexpr int NB = CHD_BAND;
-constexpr int KD = 2;               // panels per deferred-update group
-constexpr int LDV = NB * KD;        // row stride of the V / W operand arrays: [panel q = 0 | panel q = 1]
 constexpr int QR_THREADS = 256;
 constexpr int QR_S = NB + 1;        // shared-memory row stride of the panel slice
 constexpr int QR_MAXCS = 16;
@@ -488,7 +485,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
 }
 
 // ------------------------------------------------------------------ Y = A22 V
-constexpr int SY_BM = 128;
 constexpr int SY_ST = SY_BM + 8;    // transposed tile [k][i] stride (== 8 mod 16)
 constexpr int SY_SV = NB + 8;       // V chunk [k][c] stride (== 8 mod 16)
 // per k-chunk width KC (32: two CTAs per SM; 64: one CTA per SM, half the barriers per DMMA)
@@ -498,22 +494,6 @@ template <int KC> struct SymmCfg {
   static constexpr int STAGE = TILE + KC * SY_SV;
 };
 constexpr int SY_NST = 2;
-constexpr int SY_ZW = 128;          // padded width of the Z-block partials
-constexpr int SY_MAXSPLIT = 4;      // split-K factor of the symm (partial Y buffers)
-
-struct SymmArgs {
-  const double* A; size_t strideA; int ldk;
-  const double* V;   // T x n x LDV, offset to this panel's column block
-  double* Y;         // T x n x NB
-  const double* Bq;  // T x n x ldb or null
-  int ldb, nz;
-  double* Mpart;     // T x nblk x NB x NB    (nblk = row blocks x splits)
-  double* Zpart;     // T x nzblk x NB x SY_ZW (nzblk = row blocks)
-  // second panel of a deferred-update group: the first panel's V_a, W_a (T x n x LDV, column block 0) and the
-  // partials of G1 = W_a^T V, G2 = V_a^T V (T x nzblk x 2 x NB x NB); null otherwise
-  const double* Va; const double* Wa; double* Gpart;
-  int n, r0, nblk, nzblk;
-};
 
 // one staged k-chunk (SY_KC columns) of the row block: direct tile [i][k], transposed tile [k][i], optionally
 // masked against the diagonal (only the chunks that cross it)
@@ -635,76 +615,10 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: Y rows, then the partial products V_I^T Y_I and V_I^T B_I of this row block
+  // ---- epilogue: Y rows, then the partial products V_I^T Y_I, V_I^T B_I (and the group's Gram blocks)
   double* Ys = smem;                       // SY_BM x (NB + 1)
   double* Vs = Ys + SY_BM * (NB + 1);      // SY_BM x (NB + 1)
-  double* Y = a.Y + ((size_t)sp * gridDim.y + t) * n * NB;
-#pragma unroll
-  for (int x = 0; x < 2; ++x) {
-    const int rl = 16 * wid + 8 * x + fr, i = i0 + rl;
-#pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const int c = y * 8 + 2 * fk;
-      Ys[rl * (NB + 1) + c] = acc[x][y][0];
-      Ys[rl * (NB + 1) + c + 1] = acc[x][y][1];
-      if (i < n) *reinterpret_cast<double2*>(Y + (size_t)i * NB + c) = make_double2(acc[x][y][0], acc[x][y][1]);
-    }
-  }
-  for (int e = tid; e < SY_BM * NB; e += 256) {
-    const int rl = e / NB, c = e % NB;
-    Vs[rl * (NB + 1) + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
-  }
-  __syncthreads();
-  {
-    double mp[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int rl = 0; rl < SY_BM; ++rl) {
-      const double yv = Ys[rl * (NB + 1) + lane];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) mp[u] = fma(Vs[rl * (NB + 1) + wid + 8 * u], yv, mp[u]);
-    }
-    double* Mp = a.Mpart + ((size_t)t * a.nblk + bx * S + sp) * NB * NB;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) Mp[(wid + 8 * u) * NB + lane] = mp[u];
-  }
-  // deferred-update group, second panel: partials of G1 = W_a^T V and G2 = V_a^T V over this row block
-  if (a.Gpart && sp == 0) {
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      const double* src = (which == 0 ? a.Wa : a.Va) + (size_t)t * n * LDV;
-      __syncthreads();                       // Ys (Y rows, then W_a rows) has been consumed
-      for (int e = tid; e < SY_BM * NB; e += 256) {
-        const int rl = e / NB, c = e % NB;
-        Ys[rl * (NB + 1) + c] = (i0 + rl < n) ? src[(size_t)(i0 + rl) * LDV + c] : 0.0;
-      }
-      __syncthreads();
-      double gp[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int rl = 0; rl < SY_BM; ++rl) {
-        const double vv = Vs[rl * (NB + 1) + lane];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gp[u] = fma(Ys[rl * (NB + 1) + wid + 8 * u], vv, gp[u]);
-      }
-      double* Gp = a.Gpart + (((size_t)t * a.nzblk + bx) * 2 + which) * NB * NB;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) Gp[(wid + 8 * u) * NB + lane] = gp[u];
-    }
-  }
-  if (a.Bq && a.nz > 0 && sp == 0) {
-    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
-    const int z = tid & 127, c1g = tid >> 7;   // 2 groups of 16 reflector columns
-    double zp[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) zp[u] = 0.0;
-    if (z < a.nz) {
-      for (int rl = 0; rl < SY_BM && i0 + rl < n; ++rl) {
-        const double bv = Bq[(size_t)(i0 + rl) * a.ldb + z];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[rl * (NB + 1) + 16 * c1g + u], bv, zp[u]);
-      }
-    }
-    double* Zp = a.Zpart + ((size_t)t * a.nzblk + bx) * NB * SY_ZW;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
-  }
+  symm_epilogue(a, acc, Ys, Vs, tid, t, bx, sp, S, (int)gridDim.y, [] { __syncthreads(); });
 }
 
 // ------------------------------------------------------------------ fixed-order reduction of the partials
@@ -1385,11 +1299,13 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     a.Va = has_g ? bb.V : nullptr; a.Wa = has_g ? bb.W : nullptr; a.Gpart = has_g ? bb.Gpart : nullptr;
     static const int kc = getenv("CHD_SYMM_KC") ? atoi(getenv("CHD_SYMM_KC")) : 32;
     if ((rc = profile_mark_begin(PROF_SYMM, st))) return rc;
-    if (kc == 64)
+    if (pl->symm_tma) {
+      if ((rc = symm_tma_launch(pl, a, T, S, st))) return rc;
+    } else if (kc == 64)
       symm_kernel<64><<<dim3(nblk, T, S), 256, SY_NST * SymmCfg<64>::STAGE * sizeof(double), st>>>(a);
     else
       symm_kernel<32><<<dim3(nblk, T, S), 256, SY_NST * SymmCfg<32>::STAGE * sizeof(double), st>>>(a);
-    CHD_LAUNCHED();
+    if (!pl->symm_tma) CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
   }
   if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;

@@ -12,15 +12,13 @@
 //     so the HBM stream (A read + write) and the DMMA pipe overlap instead of alternating;
 //   * accumulators start at -A (read from the staged tile), results go from registers to global memory.
 // FP64 has no tcgen05 kind: DMMA m8n8k4 (mma.sync) is the FP64 tensor instruction of sm_100a.
-#include "internal.cuh"
+#include "band.cuh"
 #include "tma.cuh"
 
 namespace chd {
 
 namespace {
 
-constexpr int NB = CHD_BAND;
-constexpr int LDV = 2 * NB;          // row stride of the V / W operand arrays (band.cu: two panels side by side)
 constexpr int TM_BM = 128;           // rows of the CTA's block
 constexpr int TM_BN = 16;            // tile columns (one 16-column box)
 constexpr int TM_NST = 3;            // ring depth
@@ -184,6 +182,157 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------ Y = A22 V  (TMA + mbarrier)
+// The symmetric product from the lower triangle only, as a warp-specialised kernel: a CTA owns the 128 rows of row
+// block I and accumulates Y_I over the other row blocks P of the trailing matrix -- P < I contributes the direct block
+// A[I, P] V_P, P > I the transposed block A[P, I]^T V_P, P = I both halves of the diagonal block (masked).
+//   * PAIRED SCHEDULE: at step s the CTA of block I works on P = (s - I) mod nb; the CTA of block P works on I at the
+//     same step, i.e. both read the SAME 128 x 128 block of A (one as it is, one transposed) at the same time, so the
+//     second read hits L2: the lower triangle streams from HBM once per panel instead of twice;
+//   * tiles: direct chunks (128 rows x 32 k) as 16-column boxes with the 128-byte swizzle (conflict-free row-major
+//     fragment loads), transposed chunks (32 k x 128 rows) and the V chunks (32 k x 32) as 8-column unswizzled boxes
+//     (a DMMA fragment then reads 4 k-rows x 64 B = 256 contiguous bytes) -- all through tensor maps (UTMALDG);
+//   * 4-stage ring with mbarrier full / empty pairs, 1 producer warp + 8 DMMA consumer warps, no CTA-wide barrier in the
+//     main loop; the epilogue (Y rows + V^T Y / V^T B / Gram partials) is the one shared with the cp.async kernel.
+constexpr int SM_NST = 4;
+constexpr int SM_A_BYTES = SY_BM * 32 * 8;        // 32 KB: one chunk of A (either orientation)
+constexpr int SM_V_BYTES = 32 * NB * 8;           // 8 KB: V chunk
+constexpr int SM_STAGE = SM_A_BYTES + SM_V_BYTES;
+constexpr int SM_BAR_OFF = SM_NST * SM_STAGE;
+constexpr int SM_SMEM = SM_BAR_OFF + 64 + 1024;
+constexpr int SM_THREADS = 32 * (1 + 8);
+
+__global__ void __launch_bounds__(SM_THREADS, 1)
+symm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAt,
+                const __grid_constant__ CUtensorMap mapV, SymmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BAR_OFF);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + SM_NST;
+  const int t = blockIdx.y, I = blockIdx.x, sp = blockIdx.z, S = gridDim.z, nb = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = a.n, r0 = a.r0;
+  const int i0 = r0 + SY_BM * I;
+  // split-K over the steps: this CTA handles steps [s_lo, s_hi) of its row block
+  const int s_lo = (int)((long long)nb * sp / S), s_hi = (int)((long long)nb * (sp + 1) / S);
+  // number of chunks: 4 per step, 8 for the step that meets the diagonal block (s = 2 I mod nb)
+  int nit = 4 * (s_hi - s_lo);
+  {
+    const int sd = (2 * I) % nb;
+    if (sd >= s_lo && sd < s_hi) nit += 4;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < SM_NST; ++s) {
+      tma::mbar_init(full + s, 1);
+      tma::mbar_init(empty + s, 8);
+    }
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (wid == 0) {
+    // ===================== producer warp =====================
+    if (lane == 0) {
+      tma::prefetch_map(&mapA);
+      tma::prefetch_map(&mapAt);
+      tma::prefetch_map(&mapV);
+    }
+    int s = s_lo, rem_in_step = 0;
+    for (int it = 0; it < nit; ++it) {
+      int P = (s - I) % nb;
+      if (P < 0) P += nb;
+      const int cnt = (P == I) ? 8 : 4;
+      const bool tr = (P > I) || (P == I && rem_in_step >= 4);
+      const int c = rem_in_step & 3;
+      const int st = it % SM_NST, use = it / SM_NST;
+      if (use > 0) tma::mbar_wait(empty + st, (use - 1) & 1);
+      uint8_t* sb = sm + st * SM_STAGE;
+      const int j0 = r0 + SY_BM * P + 32 * c;          // first k index (row of V, column / row of A) of the chunk
+      if (lane == 0) tma::mbar_expect_tx(full + st, SM_STAGE);
+      __syncwarp();
+      if (lane < 16) {
+        if (!tr) {        // direct: box (bc, rb): columns j0 + 16 bc, rows i0 + 16 rb
+          const int bc = lane >> 3, rb = lane & 7;
+          tma::load_box(sb + bc * (SY_BM * 128) + rb * 2048, &mapA, j0 + 16 * bc, i0 + 16 * rb, t, full + st);
+        } else {          // transposed: box b: columns i0 + 8 b, rows j0 .. j0 + 31
+          tma::load_box(sb + lane * 2048, &mapAt, i0 + 8 * lane, j0, t, full + st);
+        }
+      } else if (lane < 20) {
+        const int y = lane - 16;                        // V chunk: columns 8 y, rows j0 .. j0 + 31
+        tma::load_box(sb + SM_A_BYTES + y * 2048, &mapV, 8 * y, j0, t, full + st);
+      }
+      if (++rem_in_step == cnt) { rem_in_step = 0; ++s; }
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  const int cw = wid - 1, ctid = tid - 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  uint32_t foff[4];                                     // direct fragment: column 4 c4 + fk of a swizzled 16-column box
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) foff[c4] = tma::swz128(fr, 4 * c4 + fk);
+  const uint32_t toff = fk * 64 + fr * 8;               // transposed / V fragment inside an 8-column box: row fk, col fr
+  double acc[2][4][2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+  {
+    int s = s_lo, rem_in_step = 0;
+    for (int it = 0; it < nit; ++it) {
+      int P = (s - I) % nb;
+      if (P < 0) P += nb;
+      const int cnt = (P == I) ? 8 : 4;
+      const bool mk = (P == I);
+      const bool tr = (P > I) || (mk && rem_in_step >= 4);
+      const int c = rem_in_step & 3;
+      if (++rem_in_step == cnt) { rem_in_step = 0; ++s; }
+      const int st = it % SM_NST, use = it / SM_NST;
+      const uint8_t* sb = sm + st * SM_STAGE;
+      const uint8_t* vb = sb + SM_A_BYTES + toff;
+      tma::mbar_wait(full + st, use & 1);
+      const int jl0 = 32 * c;                           // k offset of the chunk inside the (diagonal) block
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {                  // 8 k-steps of 4
+        double af[2], bf[4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) bf[y] = *reinterpret_cast<const double*>(vb + y * 2048 + ks * 256);
+        if (!tr) {
+          const uint8_t* ab = sb + (ks >> 2) * (SY_BM * 128) + (16 * cw) * 128 + foff[ks & 3];
+#pragma unroll
+          for (int x = 0; x < 2; ++x) af[x] = *reinterpret_cast<const double*>(ab + x * 1024);
+        } else {
+          const uint8_t* ab = sb + (2 * cw) * 2048 + ks * 256 + toff;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) af[x] = *reinterpret_cast<const double*>(ab + x * 2048);
+        }
+        if (mk) {
+          // diagonal block: the direct half keeps j <= i, the transposed half j > i (local indices inside the block)
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const int il = 16 * cw + 8 * x + fr, jl = jl0 + 4 * ks + fk;
+            if (tr ? (jl <= il) : (jl > il)) af[x] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+      }
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(empty + st);
+    }
+  }
+  // ---- epilogue (256 consumer threads; the ring is idle: every issued tile has been consumed)
+  auto csync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  csync();
+  double* Ys = reinterpret_cast<double*>(sm);
+  double* Vs = Ys + SY_BM * (NB + 1);
+  symm_epilogue(a, acc, Ys, Vs, ctid, t, I, sp, S, (int)gridDim.y, csync);
+}
+
 }  // namespace
 
 int band_tma_device_init(Plan* pl) {
@@ -192,6 +341,24 @@ int band_tma_device_init(Plan* pl) {
   if (!tma::encode_fn()) pl->syr2k_tma = 0;
   CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<1>::SMEM));
   CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<2>::SMEM));
+  pl->symm_tma = 1;
+  if (const char* e = getenv("CHD_SYMM_TMA")) pl->symm_tma = atoi(e) ? 1 : 0;
+  if (!tma::encode_fn()) pl->symm_tma = 0;
+  CHD_CUDA(cudaFuncSetAttribute(symm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+  return CHD_OK;
+}
+
+// Y = A[r0:, r0:] V with the partials of the epilogue (see SymmArgs); S = split-K factor (grid z)
+int symm_tma_launch(const Plan* pl, const SymmArgs& a, int T, int S, cudaStream_t st) {
+  const int n = pl->n, m = n - a.r0;
+  CUtensorMap mapA, mapAt, mapV;
+  int rc;
+  if ((rc = tma::make_map_f64(&mapA, a.A, (uint64_t)n, (uint64_t)n, (uint64_t)T, (uint64_t)a.ldk, 16, 16))) return rc;
+  if ((rc = tma::make_map_f64(&mapAt, a.A, (uint64_t)n, (uint64_t)n, (uint64_t)T, (uint64_t)a.ldk, 32, 8))) return rc;
+  if ((rc = tma::make_map_f64(&mapV, a.V, (uint64_t)NB, (uint64_t)n, (uint64_t)T, (uint64_t)LDV, 32, 8))) return rc;
+  const int nblk = (m + SY_BM - 1) / SY_BM;
+  symm_tma_kernel<<<dim3(nblk, T, S), SM_THREADS, SM_SMEM, st>>>(mapA, mapAt, mapV, a);
+  CHD_LAUNCHED();
   return CHD_OK;
 }
 

@@ -28,11 +28,11 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// FP64 tensor of T matrices of `rows` x `cols` elements (row stride `ld` elements), boxes of box_rows x 16 elements
-// (16 doubles = 128 B: the inner extent SWIZZLE_128B asks for), out-of-bounds elements read as zero.
-// Coordinates: {column, row, matrix}.
+// FP64 tensor of T matrices of `rows` x `cols` elements (row stride `ld` elements), boxes of box_rows x box_cols
+// elements, out-of-bounds elements read as zero.  box_cols = 16 (128 B rows) is written with SWIZZLE_128B, box_cols = 8
+// (64 B rows) unswizzled.  Coordinates: {column, row, matrix}.
 inline int make_map_f64(CUtensorMap* map, const double* base, uint64_t cols, uint64_t rows, uint64_t T, uint64_t ld,
-                        uint32_t box_rows) {
+                        uint32_t box_rows, uint32_t box_cols = 16) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -40,10 +40,12 @@ inline int make_map_f64(CUtensorMap* map, const double* base, uint64_t cols, uin
   }
   const cuuint64_t dims[3] = {cols, rows, T};
   const cuuint64_t strides[2] = {ld * sizeof(double), rows * ld * sizeof(double)};   // dims 1, 2 (bytes)
-  const cuuint32_t box[3] = {16, box_rows, 1};
+  const cuuint32_t box[3] = {box_cols, box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with code %d (cols %llu rows %llu T %llu ld %llu)", (int)r,

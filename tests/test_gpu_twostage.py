@@ -194,8 +194,10 @@ def test_regress_two_stage_matches_oracle(n, N):
 def test_deferred_group_update_equals_per_panel_update(n, tma, monkeypatch):
     """The grouped trailing update (KD = 2, default) and the per-panel update (CHD_KD=1) are the same orthogonal
     reduction: band form, Q^T S, reflectors and beta0 agree to rounding on a well-conditioned matrix -- with the
-    TMA + mbarrier trailing-update kernel (band_tma.cu, default) and with the cp.async one (CHD_SYR2K_TMA=0)."""
+    TMA + mbarrier kernels (band_tma.cu: trailing update and Y = A22 V with the paired schedule; default) and with the
+    cp.async ones (CHD_SYR2K_TMA=0, CHD_SYMM_TMA=0)."""
     monkeypatch.setenv("CHD_SYR2K_TMA", tma)
+    monkeypatch.setenv("CHD_SYMM_TMA", tma)
     nat = _native()
     rng = np.random.default_rng(9)
     F = rng.standard_normal((n, n))
