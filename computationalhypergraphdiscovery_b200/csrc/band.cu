@@ -615,11 +615,85 @@ __global__ void __launch_bounds__(256, KC == 32 ? 2 : 1) symm_kernel(SymmArgs a)
   }
   cp_async_wait<0>();
 
-  // ---- epilogue: Y rows, then the partial products V_I^T Y_I, V_I^T B_I (and the group's Gram blocks)
+  // ---- epilogue: the Y rows of this split-K partial (the products with V / B follow in symm_partials_kernel)
+  symm_store_y(a, acc, tid, t, bx, sp, (int)gridDim.y);
+}
+
+// ------------------------------------------------------------------ partial products of a row block
+// One CTA per 128-row block: sums the split-K partials of Y (result back into buffer 0), then
+//   Mpart = V_I^T Y_I,  Zpart = V_I^T B_I,  and for the second panel of a group  Gpart = {W_a,I^T V_I, V_a,I^T V_I};
+// reduce_kernel adds the blocks in fixed order (deterministic, no atomics).
+__global__ void __launch_bounds__(256) symm_partials_kernel(SymmArgs a) {
+  extern __shared__ __align__(16) double smem[];
   double* Ys = smem;                       // SY_BM x (NB + 1)
   double* Vs = Ys + SY_BM * (NB + 1);      // SY_BM x (NB + 1)
-  symm_epilogue(a, acc, Ys, Vs, tid, t, bx, sp, S, (int)gridDim.y, [] { __syncthreads(); });
+  const int t = blockIdx.y, bx = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = a.n, i0 = a.r0 + SY_BM * bx;
+  const double* V = a.V + (size_t)t * n * LDV;
+  double* Y0 = a.Y + (size_t)t * n * NB;
+  for (int e = tid; e < SY_BM * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    const bool ok = i0 + rl < n;
+    double yv = 0.0;
+    if (ok) {
+      for (int sp = 0; sp < a.nsplit; ++sp) yv += a.Y[((size_t)sp * a.T + t) * n * NB + (size_t)(i0 + rl) * NB + c];
+      if (a.nsplit > 1) Y0[(size_t)(i0 + rl) * NB + c] = yv;
+    }
+    Ys[rl * (NB + 1) + c] = yv;
+    Vs[rl * (NB + 1) + c] = ok ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
+  }
+  __syncthreads();
+  {
+    double mp[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int rl = 0; rl < SY_BM; ++rl) {
+      const double yv = Ys[rl * (NB + 1) + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mp[u] = fma(Vs[rl * (NB + 1) + wid + 8 * u], yv, mp[u]);
+    }
+    double* Mp = a.Mpart + ((size_t)t * a.nblk + bx) * NB * NB;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Mp[(wid + 8 * u) * NB + lane] = mp[u];
+  }
+  if (a.Gpart) {
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const double* src = (which == 0 ? a.Wa : a.Va) + (size_t)t * n * LDV;
+      __syncthreads();                       // Ys (Y rows, then W_a rows) has been consumed
+      for (int e = tid; e < SY_BM * NB; e += 256) {
+        const int rl = e / NB, c = e % NB;
+        Ys[rl * (NB + 1) + c] = (i0 + rl < n) ? src[(size_t)(i0 + rl) * LDV + c] : 0.0;
+      }
+      __syncthreads();
+      double gp[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int rl = 0; rl < SY_BM; ++rl) {
+        const double vv = Vs[rl * (NB + 1) + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gp[u] = fma(Ys[rl * (NB + 1) + wid + 8 * u], vv, gp[u]);
+      }
+      double* Gp = a.Gpart + (((size_t)t * a.nblk + bx) * 2 + which) * NB * NB;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Gp[(wid + 8 * u) * NB + lane] = gp[u];
+    }
+  }
+  if (a.Bq && a.nz > 0) {
+    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
+    const int z = tid & 127, c1g = tid >> 7;   // 2 groups of 16 reflector columns
+    double zp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) zp[u] = 0.0;
+    if (z < a.nz) {
+      for (int rl = 0; rl < SY_BM && i0 + rl < n; ++rl) {
+        const double bv = Bq[(size_t)(i0 + rl) * a.ldb + z];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[rl * (NB + 1) + 16 * c1g + u], bv, zp[u]);
+      }
+    }
+    double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
+  }
 }
+constexpr size_t SP_SMEM = (size_t)2 * SY_BM * (NB + 1) * sizeof(double);
 
 // ------------------------------------------------------------------ fixed-order reduction of the partials
 struct ReduceArgs {
@@ -627,7 +701,7 @@ struct ReduceArgs {
   double* Mred;   // T x NB x NB
   double* Zred;   // T x NB x SY_ZW
   double* Gred;   // T x 2 x NB x NB
-  int nblk, nzblk, has_z, has_g;
+  int nblk, has_z, has_g;
 };
 
 __global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
@@ -642,15 +716,15 @@ __global__ void __launch_bounds__(256) reduce_kernel(ReduceArgs a) {
   } else if (e < NM + NZ) {
     if (!a.has_z) return;
     const int ez = e - NM;
-    const double* p = a.Zpart + (size_t)t * a.nzblk * NZ + ez;
+    const double* p = a.Zpart + (size_t)t * a.nblk * NZ + ez;
     double s = 0.0;
-    for (int b = 0; b < a.nzblk; ++b) s += p[(size_t)b * NZ];
+    for (int b = 0; b < a.nblk; ++b) s += p[(size_t)b * NZ];
     a.Zred[(size_t)t * NZ + ez] = s;
   } else if (e < NM + NZ + 2 * NM && a.has_g) {
     const int eg = e - NM - NZ;
-    const double* p = a.Gpart + (size_t)t * a.nzblk * 2 * NM + eg;
+    const double* p = a.Gpart + (size_t)t * a.nblk * 2 * NM + eg;
     double s = 0.0;
-    for (int b = 0; b < a.nzblk; ++b) s += p[(size_t)b * 2 * NM];
+    for (int b = 0; b < a.nblk; ++b) s += p[(size_t)b * 2 * NM];
     a.Gred[(size_t)t * 2 * NM + eg] = s;
   }
 }
@@ -1295,7 +1369,7 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
   {
     SymmArgs a;
     a.A = K; a.strideA = strideA; a.ldk = ldk; a.V = Vq; a.Y = bb.Y; a.Bq = B; a.ldb = ldb; a.nz = nz;
-    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk * S; a.nzblk = nblk;
+    a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.n = n; a.r0 = r0; a.nblk = nblk; a.nsplit = S; a.T = T;
     a.Va = has_g ? bb.V : nullptr; a.Wa = has_g ? bb.W : nullptr; a.Gpart = has_g ? bb.Gpart : nullptr;
     static const int kc = getenv("CHD_SYMM_KC") ? atoi(getenv("CHD_SYMM_KC")) : 32;
     if ((rc = profile_mark_begin(PROF_SYMM, st))) return rc;
@@ -1307,12 +1381,14 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
       symm_kernel<32><<<dim3(nblk, T, S), 256, SY_NST * SymmCfg<32>::STAGE * sizeof(double), st>>>(a);
     if (!pl->symm_tma) CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
+    if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
+    symm_partials_kernel<<<dim3(nblk, T), 256, SP_SMEM, st>>>(a);
+    CHD_LAUNCHED();
   }
-  if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
   {
     ReduceArgs a;
     a.Mpart = bb.Mpart; a.Zpart = bb.Zpart; a.Gpart = bb.Gpart; a.Mred = bb.Mred; a.Zred = bb.Zred; a.Gred = bb.Gred;
-    a.nblk = nblk * S; a.nzblk = nblk; a.has_z = has_z ? 1 : 0; a.has_g = has_g ? 1 : 0;
+    a.nblk = nblk; a.has_z = has_z ? 1 : 0; a.has_g = has_g ? 1 : 0;
     const int total = NB * NB + NB * SY_ZW + (has_g ? 2 * NB * NB : 0);
     reduce_kernel<<<dim3((total + 255) / 256, T), 256, 0, st>>>(a);
     CHD_LAUNCHED();
@@ -1326,7 +1402,7 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
   }
   {
     WformArgs a;
-    a.V = Vq; a.Y = bb.Y; a.W = bb.W + q * NB; a.nsplit = S; a.T = T;
+    a.V = Vq; a.Y = bb.Y; a.W = bb.W + q * NB; a.nsplit = 1; a.T = T;   // split partials already summed
     a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride; a.TM = bb.TM;
     a.Gred = has_g ? bb.Gred : nullptr; a.Va = bb.V; a.Wa = bb.W; a.n = n; a.r0 = r0;
     wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
@@ -1374,6 +1450,7 @@ int band_device_init(Plan* pl) {
   CHD_CUDA(cudaFuncSetAttribute(symm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(SY_NST * SymmCfg<64>::STAGE * sizeof(double))));
   CHD_CUDA(cudaFuncSetAttribute(wform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(symm_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(zupdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZU_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -18,92 +18,33 @@ struct SymmArgs {
   double* Y;         // T x n x NB
   const double* Bq;  // T x n x ldb or null
   int ldb, nz;
-  double* Mpart;     // T x nblk x NB x NB    (nblk = row blocks x splits)
-  double* Zpart;     // T x nzblk x NB x SY_ZW (nzblk = row blocks)
+  double* Mpart;     // T x nblk x NB x NB     (nblk = row blocks)
+  double* Zpart;     // T x nblk x NB x SY_ZW
   // second panel of a deferred-update group: the first panel's V_a, W_a (T x n x LDV, column block 0) and the
-  // partials of G1 = W_a^T V, G2 = V_a^T V (T x nzblk x 2 x NB x NB); null otherwise
+  // partials of G1 = W_a^T V, G2 = V_a^T V (T x nblk x 2 x NB x NB); null otherwise
   const double* Va; const double* Wa; double* Gpart;
-  int n, r0, nblk, nzblk;
+  int n, r0, nblk;
+  int nsplit, T;     // split-K partial buffers of Y (summed into buffer 0 by symm_partials_kernel), targets
 };
 
 // Epilogue shared by both symm kernels, run by 256 threads (ctid = 0..255, 8 warps) that hold the 128 x 32 block of Y
-// in DMMA accumulator layout (warp w: rows 16 w + 8 x + fr, columns 8 y + 2 fk + {0,1}): stores the Y rows (split-K
-// partial `sp` of `S`), then the partial products of this row block: V_I^T Y_I (Mpart), V_I^T B_I (Zpart, sp == 0)
-// and, for the second panel of a group, W_a^T V and V_a^T V (Gpart, sp == 0).  Ys, Vs: SY_BM x (NB + 1) doubles of
-// shared memory each; `sync` synchronises the 256 threads.
-template <class Sync>
-__device__ __forceinline__ void symm_epilogue(const SymmArgs& a, const double (&acc)[2][4][2], double* Ys, double* Vs,
-                                              int ctid, int t, int bx, int sp, int S, int T, Sync sync) {
+// in DMMA accumulator layout (warp w: rows 16 w + 8 x + fr, columns 8 y + 2 fk + {0,1}): stores the Y rows of split-K
+// partial `sp`.  The products of the row block with V, B and the group's first panel (V^T Y, V^T B, Gram blocks) are
+// computed by symm_partials_kernel, at full occupancy, instead of at the tail of every GEMM CTA.
+__device__ __forceinline__ void symm_store_y(const SymmArgs& a, const double (&acc)[2][4][2], int ctid, int t, int bx,
+                                             int sp, int T) {
   const int lane = ctid & 31, wid = ctid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int n = a.n, i0 = a.r0 + SY_BM * bx;
-  const double* V = a.V + (size_t)t * n * LDV;
   double* Y = a.Y + ((size_t)sp * T + t) * n * NB;
 #pragma unroll
   for (int x = 0; x < 2; ++x) {
-    const int rl = 16 * wid + 8 * x + fr, i = i0 + rl;
+    const int i = i0 + 16 * wid + 8 * x + fr;
+    if (i < n) {
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const int c = y * 8 + 2 * fk;
-      Ys[rl * (NB + 1) + c] = acc[x][y][0];
-      Ys[rl * (NB + 1) + c + 1] = acc[x][y][1];
-      if (i < n) *reinterpret_cast<double2*>(Y + (size_t)i * NB + c) = make_double2(acc[x][y][0], acc[x][y][1]);
+      for (int y = 0; y < 4; ++y)
+        *reinterpret_cast<double2*>(Y + (size_t)i * NB + y * 8 + 2 * fk) = make_double2(acc[x][y][0], acc[x][y][1]);
     }
-  }
-  for (int e = ctid; e < SY_BM * NB; e += 256) {
-    const int rl = e / NB, c = e % NB;
-    Vs[rl * (NB + 1) + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
-  }
-  sync();
-  {
-    double mp[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int rl = 0; rl < SY_BM; ++rl) {
-      const double yv = Ys[rl * (NB + 1) + lane];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) mp[u] = fma(Vs[rl * (NB + 1) + wid + 8 * u], yv, mp[u]);
-    }
-    double* Mp = a.Mpart + ((size_t)t * a.nblk + bx * S + sp) * NB * NB;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) Mp[(wid + 8 * u) * NB + lane] = mp[u];
-  }
-  // deferred-update group, second panel: partials of G1 = W_a^T V and G2 = V_a^T V over this row block
-  if (a.Gpart && sp == 0) {
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      const double* src = (which == 0 ? a.Wa : a.Va) + (size_t)t * n * LDV;
-      sync();                                // Ys (Y rows, then W_a rows) has been consumed
-      for (int e = ctid; e < SY_BM * NB; e += 256) {
-        const int rl = e / NB, c = e % NB;
-        Ys[rl * (NB + 1) + c] = (i0 + rl < n) ? src[(size_t)(i0 + rl) * LDV + c] : 0.0;
-      }
-      sync();
-      double gp[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int rl = 0; rl < SY_BM; ++rl) {
-        const double vv = Vs[rl * (NB + 1) + lane];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gp[u] = fma(Ys[rl * (NB + 1) + wid + 8 * u], vv, gp[u]);
-      }
-      double* Gp = a.Gpart + (((size_t)t * a.nzblk + bx) * 2 + which) * NB * NB;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) Gp[(wid + 8 * u) * NB + lane] = gp[u];
-    }
-  }
-  if (a.Bq && a.nz > 0 && sp == 0) {
-    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
-    const int z = ctid & 127, c1g = ctid >> 7;   // 2 groups of 16 reflector columns
-    double zp[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) zp[u] = 0.0;
-    if (z < a.nz) {
-      for (int rl = 0; rl < SY_BM && i0 + rl < n; ++rl) {
-        const double bv = Bq[(size_t)(i0 + rl) * a.ldb + z];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[rl * (NB + 1) + 16 * c1g + u], bv, zp[u]);
-      }
-    }
-    double* Zp = a.Zpart + ((size_t)t * a.nzblk + bx) * NB * SY_ZW;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
   }
 }
 

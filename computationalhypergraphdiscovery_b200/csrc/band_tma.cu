@@ -193,18 +193,20 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 //     fragment loads), transposed chunks (32 k x 128 rows) and the V chunks (32 k x 32) as 8-column unswizzled boxes
 //     (a DMMA fragment then reads 4 k-rows x 64 B = 256 contiguous bytes) -- all through tensor maps (UTMALDG);
 //   * 4-stage ring with mbarrier full / empty pairs, 1 producer warp + 8 DMMA consumer warps, no CTA-wide barrier in the
-//     main loop; the epilogue (Y rows + V^T Y / V^T B / Gram partials) is the one shared with the cp.async kernel.
-constexpr int SM_NST = 4;
+//     main loop; the epilogue only stores the Y rows (the V^T Y / V^T B / Gram partials: symm_partials_kernel).
 constexpr int SM_A_BYTES = SY_BM * 32 * 8;        // 32 KB: one chunk of A (either orientation)
 constexpr int SM_V_BYTES = 32 * NB * 8;           // 8 KB: V chunk
 constexpr int SM_STAGE = SM_A_BYTES + SM_V_BYTES;
-constexpr int SM_BAR_OFF = SM_NST * SM_STAGE;
-constexpr int SM_SMEM = SM_BAR_OFF + 64 + 1024;
 constexpr int SM_THREADS = 32 * (1 + 8);
+// SM_NST stages per CTA: 4 with one CTA per SM, 2 with two CTAs per SM (16 consumer warps per SM, the epilogue and the
+// pipeline fill of one CTA overlap with the other's main loop)
+template <int SM_NST> constexpr int symm_tma_smem() { return SM_NST * SM_STAGE + 64 + 1024; }
 
-__global__ void __launch_bounds__(SM_THREADS, 1)
+template <int SM_NST>
+__global__ void __launch_bounds__(SM_THREADS, SM_NST == 2 ? 2 : 1)
 symm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAt,
                 const __grid_constant__ CUtensorMap mapV, SymmArgs a) {
+  constexpr int SM_BAR_OFF = SM_NST * SM_STAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BAR_OFF);
@@ -325,12 +327,8 @@ symm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (lane == 0) tma::mbar_arrive(empty + st);
     }
   }
-  // ---- epilogue (256 consumer threads; the ring is idle: every issued tile has been consumed)
-  auto csync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-  csync();
-  double* Ys = reinterpret_cast<double*>(sm);
-  double* Vs = Ys + SY_BM * (NB + 1);
-  symm_epilogue(a, acc, Ys, Vs, ctid, t, I, sp, S, (int)gridDim.y, csync);
+  // ---- epilogue: the Y rows of this split-K partial, straight from the accumulators
+  symm_store_y(a, acc, ctid, t, I, sp, (int)gridDim.y);
 }
 
 }  // namespace
@@ -344,7 +342,10 @@ int band_tma_device_init(Plan* pl) {
   pl->symm_tma = 1;
   if (const char* e = getenv("CHD_SYMM_TMA")) pl->symm_tma = atoi(e) ? 1 : 0;
   if (!tma::encode_fn()) pl->symm_tma = 0;
-  CHD_CUDA(cudaFuncSetAttribute(symm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+  pl->symm_tma_ctas = 2;
+  if (const char* e = getenv("CHD_SYMM_TMA_CTAS")) pl->symm_tma_ctas = atoi(e) == 1 ? 1 : 2;
+  CHD_CUDA(cudaFuncSetAttribute(symm_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, symm_tma_smem<4>()));
+  CHD_CUDA(cudaFuncSetAttribute(symm_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, symm_tma_smem<2>()));
   return CHD_OK;
 }
 
@@ -357,7 +358,10 @@ int symm_tma_launch(const Plan* pl, const SymmArgs& a, int T, int S, cudaStream_
   if ((rc = tma::make_map_f64(&mapAt, a.A, (uint64_t)n, (uint64_t)n, (uint64_t)T, (uint64_t)a.ldk, 32, 8))) return rc;
   if ((rc = tma::make_map_f64(&mapV, a.V, (uint64_t)NB, (uint64_t)n, (uint64_t)T, (uint64_t)LDV, 32, 8))) return rc;
   const int nblk = (m + SY_BM - 1) / SY_BM;
-  symm_tma_kernel<<<dim3(nblk, T, S), SM_THREADS, SM_SMEM, st>>>(mapA, mapAt, mapV, a);
+  if (pl->symm_tma_ctas == 2)
+    symm_tma_kernel<2><<<dim3(nblk, T, S), SM_THREADS, symm_tma_smem<2>(), st>>>(mapA, mapAt, mapV, a);
+  else
+    symm_tma_kernel<4><<<dim3(nblk, T, S), SM_THREADS, symm_tma_smem<4>(), st>>>(mapA, mapAt, mapV, a);
   CHD_LAUNCHED();
   return CHD_OK;
 }

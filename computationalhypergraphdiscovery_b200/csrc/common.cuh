@@ -48,6 +48,7 @@ struct Plan {
   int qr_reg_max_cs;       // largest cluster of the register-resident panel QR (0: disabled)
   int gauss_shared;        // 1: Gaussian activations of a batch share the per-pair factors (gauss_shared_kernel)
   int band_kd;             // panels per deferred trailing update of the dense -> band stage (1 or 2)
+  int symm_tma_ctas;       // CTAs per SM of the TMA symm kernel (2: two 2-stage rings, 1: one 4-stage ring)
   int symm_tma;            // 1: TMA + mbarrier warp-specialised Y = A22 V with the paired block schedule
   int syr2k_tma;           // 1: TMA + mbarrier warp-specialised trailing update (band_tma.cu), 0: cp.async kernel
 };
