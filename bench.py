@@ -249,10 +249,10 @@ def run_b200(args):
     X, _names = make_data(n, N, seed=0)
     X = np.ascontiguousarray((X - X.mean(0)) / X.std(0))
     plan0 = _native.Plan(n, N, N)
-    # two-stage path: every launch is batched over the targets in flight (32 per kernel state: 17 GB of work
-    # matrices at n = 8192; the latency-bound kernels -- bulge chasing, panel QR -- amortise over them);
-    # one-stage path: one cooperative wave
-    Tb = args.targets or (min(32, max(1, N)) if plan0.two_stage else plan0.matrices_per_wave)
+    # two-stage path: every launch is batched over the targets in flight (64 per kernel state: 34 GB of work
+    # matrices at n = 8192; the latency-bound kernels -- bulge chasing, panel QR -- and the small last panels of the
+    # GEMMs amortise over them: 42.4 ms per regression at 64 in flight, 44.4 at 32); one-stage path: one wave
+    Tb = args.targets or (min(64, max(1, N)) if plan0.two_stage else plan0.matrices_per_wave)
     Xd = torch.from_numpy(X).to(dev)
     cl = torch.arange(N, dtype=torch.int32, device=dev)
     descs = {"linear": _native.make_desc(0, 2.0), "quadratic": _native.make_desc(1, 1.0, alpha=1.0),

@@ -682,10 +682,16 @@ __global__ void __launch_bounds__(256) symm_partials_kernel(SymmArgs a) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) zp[u] = 0.0;
     if (z < a.nz) {
-      for (int rl = 0; rl < SY_BM && i0 + rl < n; ++rl) {
-        const double bv = Bq[(size_t)(i0 + rl) * a.ldb + z];
+      // batches of 8 rows: the 8 loads of a batch are in flight together (rows beyond n read as zero)
+#pragma unroll 1
+      for (int rb = 0; rb < SY_BM; rb += 8) {
+        double bv[8];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[rl * (NB + 1) + 16 * c1g + u], bv, zp[u]);
+        for (int q = 0; q < 8; ++q) bv[q] = (i0 + rb + q < n) ? Bq[(size_t)(i0 + rb + q) * a.ldb + z] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[(rb + q) * (NB + 1) + 16 * c1g + u], bv[q], zp[u]);
       }
     }
     double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW;
