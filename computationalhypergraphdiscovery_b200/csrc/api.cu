@@ -253,6 +253,7 @@ extern "C" int chd_plan_create(chd_plan** plan, int n, int N, int C, int device,
     if (!rc) rc = chase_device_init(pl);
     if (!rc) rc = tridiag_device_init(pl);
     if (!rc) rc = act_device_init(pl);
+    pl->gram_downdate = getenv("CHD_GRAM_DOWNDATE") ? atoi(getenv("CHD_GRAM_DOWNDATE")) : 1;
     if (cur != device) cudaSetDevice(cur);
     if (rc) {
       delete pl;
@@ -294,6 +295,7 @@ extern "C" size_t chd_workspace_bytes(const chd_plan* plan, int T) {
   b += align_up(T * n * ldk * sizeof(double), 256);  // K work matrices (prune chain)
   b += 3 * align_up((size_t)T * pl->N, 256);         // active / previous / removed variable masks
   b += gb + act_workspace(pl, T);
+  b += gram_full_core_bytes(pl);                     // shared linear core G = X X^T (downdate mode of the Gram)
   return b + 8192;
 }
 
@@ -354,12 +356,21 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
   char* gws = cv.take<char>(gb);
   const size_t ab = act_workspace(pl, T);
   char* aws = cv.take<char>(ab);
+  double* Gfull = cv.take<double>((size_t)n * ldk);
+  uint8_t* ones = cv.take<uint8_t>((size_t)N);
   if (!ok || !cv.ok) {
     set_error("chd_prune_chain: workspace too small (%zu needed, %zu given)", cv.off, workspace_bytes);
     return CHD_ENOSPC;
   }
   if (ldk > n) CHD_CUDA(cudaMemsetAsync(K, 0, (size_t)T * n * ldk * sizeof(double), st));
   int rc;
+  // shared linear core of the full variable set: every step's Gram is a rank-r downdate of it while a target has
+  // fewer removed than active variables (gram.cu); one extra Gram per call, amortised over T targets x steps
+  const double* Gf = nullptr;
+  if (pl->gram_downdate && steps > 0 && (long long)T * steps >= 4) {
+    if ((rc = gram_full_core_launch(pl, X, Gfull, ldk, ones, gws, gb, st))) return rc;
+    Gf = Gfull;
+  }
   for (int s = 0; s < steps; ++s) {
     const long long step = (long long)first_step + s;
     const long long p = (long long)N - step - 1;
@@ -389,9 +400,9 @@ extern "C" int chd_prune_chain(const chd_plan* plan, const chd_kernel_desc* kd, 
     if ((rc = active_vars_launch(w0, alive, cluster_of, N, C, T, w, st))) return rc;
     if (use_p) {
       if ((rc = removed_vars_launch(wprev, w, T * N, wrem, st))) return rc;
-      if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st, P_state, 2, wrem))) return rc;
+      if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st, P_state, 2, wrem, Gf))) return rc;
     } else {
-      if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st, nullptr, 0, nullptr))) return rc;
+      if ((rc = gram_launch(pl, kd, X, X, n, w, T, K, ldk, gws, gb, st, nullptr, 0, nullptr, Gf))) return rc;
     }
     if ((rc = regress_core(pl, K, ldk, ga, T, gamma_grid, 0, 0.0, gamma_min, keys, keys, is_refresh(step + 1),
                            lambda_min, yb, (size_t)n, noise + s, z_low + s, z_high + s, gamma + s, (size_t)steps,

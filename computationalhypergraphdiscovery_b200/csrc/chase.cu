@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) 
   const int t = blockIdx.y, n = a.n;
   double* bw = a.bandW + (size_t)t * n * CLD;
   int* prog = a.prog + (size_t)t * n;
-  __shared__ int s_j, s_ok;
+  __shared__ int s_j, s_ok, s_seen;
   double* D = smem;                    // CB x CS_
   double* S = D + CB * CS_;            // CB x CS_
   double* vs = S + CB * CS_;           // CB
@@ -220,13 +220,21 @@ __global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) 
     int h = 0;
     // returns false when the predecessor never got there (a bug or a dead context): flag it and let the host see
     // NaN results instead of trapping the whole context
+    // `seen` = the predecessor's progress at the last look (uniform over the CTA): as long as it covers the hop we
+    // are about to start, neither the acquire load (an L2 round trip on the critical path of every hop) nor the
+    // barrier that broadcasts it is needed -- the release that published `seen` already ordered everything before it
+    int seen = (j == 0) ? CH_DONE : 0;
     auto wait_prev = [&](int need) -> bool {
-      if (j > 0 && tid == 0) {
+      if (seen >= need) return true;
+      if (tid == 0) {
         unsigned long long spins = 0;
-        while (ld_acquire(prog + j - 1) < need)
+        int v;
+        while ((v = ld_acquire(prog + j - 1)) < need)
           if (++spins > CH_SPIN_LIMIT) { s_ok = 0; atomicExch(a.err, 1); break; }
+        s_seen = v;
       }
       __syncthreads();
+      seen = s_seen;
       return s_ok != 0;
     };
     bool alive = wait_prev(2);

@@ -46,6 +46,7 @@ struct Plan {
   int chase_wave;          // cap on matrices per bulge-chasing launch (0: none)
   size_t chase_l2_budget;  // bytes of work bands one bulge-chasing launch may touch
   int qr_reg_max_cs;       // largest cluster of the register-resident panel QR (0: disabled)
+  int gram_downdate;       // 1: Gram cores as rank-r downdates of the shared G = X X^T when r < p
   int gauss_shared;        // 1: Gaussian activations of a batch share the per-pair factors (gauss_shared_kernel)
   int band_kd;             // panels per deferred trailing update of the dense -> band stage (1 or 2)
   int symm_tma_ctas;       // CTAs per SM of the TMA symm kernel (2: two 2-stage rings, 1: one 4-stage ring)

@@ -8,13 +8,18 @@
 //                      quadratic s (alpha + L)^2 + 1 - alpha^2 s      (Modes/kernels.py:169-173)
 //                      gaussian  s prod_d (1 + exp(-(x_d-y_d)^2/2l^2)) + quad - 1   (Modes/kernels.py:251-257)
 //                    The n x n x N `exps` tensor of the reference (kernels.py:307-309) is never formed.
+//   DOWNDATE mode   : the linear core of the full variable set G = X X^T does not depend on the target.  When a
+//                    target has fewer REMOVED than active variables (always, in the first half of a prune chain),
+//                    its core is L = G - X_r X_r^T with the removed columns X_r gathered instead of the active ones:
+//                    2 n^2 r flop (r = 1 in stage 1, r = steps so far in a chain) instead of 2 n^2 p.  G is computed
+//                    once per chd_gram / chd_prune_chain call into the caller's workspace.
 #include "internal.cuh"
 
 namespace chd {
 
 __global__ void compact_kernel(const uint8_t* __restrict__ w, int N, int ldi, int32_t* __restrict__ idx,
-                               int32_t* __restrict__ pcount) {
-  // one warp per target
+                               int32_t* __restrict__ pcount, int invert = 0) {
+  // one warp per target; invert: list the variables with w == 0 instead
   const int t = blockIdx.x;
   const int lane = threadIdx.x;
   const uint8_t* wt = w + (size_t)t * N;
@@ -22,12 +27,26 @@ __global__ void compact_kernel(const uint8_t* __restrict__ w, int N, int ldi, in
   int base = 0;
   for (int d0 = 0; d0 < N; d0 += 32) {
     int d = d0 + lane;
-    bool on = (d < N) && (wt[d] != 0);
+    bool on = (d < N) && ((wt[d] != 0) != (invert != 0));
     unsigned m = __ballot_sync(0xffffffffu, on);
     if (on) it[base + __popc(m & ((1u << lane) - 1u))] = d;
     base += __popc(m);
   }
   if (lane == 0) pcount[t] = base;
+}
+
+// per target: pick the shorter of the active / removed variable lists (down[t] = 1: removed list, L = G - X_r X_r^T)
+__global__ void choose_list_kernel(const int32_t* __restrict__ idx_act, const int32_t* __restrict__ cnt_act,
+                                   const int32_t* __restrict__ idx_rem, const int32_t* __restrict__ cnt_rem, int ldi,
+                                   int allow_down, int32_t* __restrict__ idx_sel, int32_t* __restrict__ cnt_sel,
+                                   int32_t* __restrict__ down) {
+  const int t = blockIdx.x;
+  const int pa = cnt_act[t], pr = cnt_rem[t];
+  const bool dn = allow_down && pr < pa;
+  const int32_t* src = (dn ? idx_rem : idx_act) + (size_t)t * ldi;
+  const int cnt = dn ? pr : pa;
+  for (int q = threadIdx.x; q < cnt; q += blockDim.x) idx_sel[(size_t)t * ldi + q] = src[q];
+  if (threadIdx.x == 0) { cnt_sel[t] = cnt; down[t] = dn ? 1 : 0; }
 }
 
 __global__ void gather_kernel(const double* __restrict__ X, int n, int N, const int32_t* __restrict__ idx, int ldi,
@@ -43,6 +62,7 @@ __global__ void gather_kernel(const double* __restrict__ X, int n, int N, const 
   }
 }
 
+constexpr int CHD_KERNEL_RAW = 99;   // internal: K = L (the linear core itself), used for the shared G = X X^T
 constexpr int GT = 64;        // CTA tile (GT x GT)
 constexpr int GK = 32;        // k chunk
 constexpr int GS = GK + 4;    // smem row stride (== 4 mod 8 -> conflict-free DMMA fragment loads)
@@ -54,7 +74,9 @@ __global__ void __launch_bounds__(256, 2) gram_kernel(const double* __restrict__
                                                    int nq, int n, int ldp, const int32_t* __restrict__ pcount,
                                                    double* __restrict__ K, int ldk, chd_kernel_desc kd,
                                                    double* __restrict__ P, int pmode,
-                                                   const double* __restrict__ Xr, const int32_t* __restrict__ rcount) {
+                                                   const double* __restrict__ Xr, const int32_t* __restrict__ rcount,
+                                                   const double* __restrict__ Gfull,
+                                                   const int32_t* __restrict__ down) {
   // Gaussian product-map cache P = prod_{d active}(1 + E_d):
   //   pmode 0: no cache;  1: compute the product and store it in P (K may be null: product only);
   //   2: P <- P / prod_{d removed}(1 + E_d) with the removed variables gathered in Xr (n x ldp), no full product.
@@ -77,6 +99,7 @@ __global__ void __launch_bounds__(256, 2) gram_kernel(const double* __restrict__
     bj = blockIdx.x - bi * tiles_j;
   }
   const int p = pcount[t];
+  const bool dn = Gfull && down && down[t];      // gathered columns are the REMOVED ones: L = G - acc
   const double* A = XcA + (size_t)t * nq * ldp;
   const double* B = XcB + (size_t)t * n * ldp;
   double* Kt = K + (size_t)t * nq * ldk;
@@ -137,7 +160,7 @@ __global__ void __launch_bounds__(256, 2) gram_kernel(const double* __restrict__
 #pragma unroll
         for (int b = 0; b < 2; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
-    if (gauss && pmode != 2) {
+    if (gauss && pmode != 2 && !dn) {
       const int dmax = min(GK, p - k0);
       for (int dd = 0; dd < dmax; ++dd) {
         double xr[4], xc[2][2];
@@ -206,9 +229,12 @@ __global__ void __launch_bounds__(256, 2) gram_kernel(const double* __restrict__
       double v[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const double L = acc[a][b][c];
+        double L = acc[a][b][c];
+        if (dn) L = ((i < nq) && (j + c < n)) ? Gfull[(size_t)i * ldk + j + c] - L : 0.0;
         double r;
-        if (kd.kind == CHD_KERNEL_LINEAR) {
+        if (kd.kind == CHD_KERNEL_RAW) {
+          r = L;
+        } else if (kd.kind == CHD_KERNEL_LINEAR) {
           r = 1.0 + s * L;
         } else if (kd.kind == CHD_KERNEL_QUADRATIC) {
           const double u = al + L;
@@ -274,6 +300,8 @@ int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes) {
   b += align_up((size_t)T * sizeof(int32_t), 256);
   b += 2 * align_up((size_t)T * pl->n * ldp * sizeof(double), 256);   // Xc and the removed-variable gather
   b += align_up((size_t)T * pl->N * sizeof(int32_t), 256) + align_up((size_t)T * sizeof(int32_t), 256);
+  b += 2 * (align_up((size_t)T * pl->N * sizeof(int32_t), 256) + align_up((size_t)T * sizeof(int32_t), 256));  // removed / chosen lists
+  b += align_up((size_t)T * sizeof(int32_t), 256);                                                            // down flags
   if (nq >= 0) b += align_up((size_t)T * nq * ldp * sizeof(double), 256);
   *bytes = b + 1024;
   return ldp;
@@ -281,7 +309,7 @@ int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes) {
 
 int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
                 const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st,
-                double* P, int pmode, const uint8_t* wrem) {
+                double* P, int pmode, const uint8_t* wrem, const double* Gfull) {
   const int n = pl->n, N = pl->N;
   const bool symm = (Xq == X) && (nq == n);
   Carver cv(ws, ws_bytes);
@@ -292,8 +320,16 @@ int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, cons
   double* Xr = cv.take<double>((size_t)T * n * ldp);
   int32_t* idx2 = cv.take<int32_t>((size_t)T * N);
   int32_t* pc2 = cv.take<int32_t>(T);
+  int32_t* idx_rem = cv.take<int32_t>((size_t)T * N);
+  int32_t* cnt_rem = cv.take<int32_t>(T);
+  int32_t* idx_sel = cv.take<int32_t>((size_t)T * N);
+  int32_t* cnt_sel = cv.take<int32_t>(T);
+  int32_t* down = cv.take<int32_t>(T);
   double* Xqc = symm ? Xc : cv.take<double>((size_t)T * nq * ldp);
   if (kd->kind != CHD_KERNEL_GAUSSIAN || !P) pmode = 0;
+  // downdate from the shared full-set core: symmetric train Gram only; a Gaussian full product (no cached map, or a
+  // rebuild of it) needs the active columns staged, so it keeps the direct form
+  if (!symm || (kd->kind == CHD_KERNEL_GAUSSIAN && pmode != 2)) Gfull = nullptr;
   if (pmode == 2 && (!symm || !wrem)) return CHD_EINVAL;
   if (!cv.ok) {
     set_error("chd_gram: workspace too small (%zu needed, %zu given)", cv.off, ws_bytes);
@@ -301,6 +337,14 @@ int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, cons
   }
   compact_kernel<<<T, 32, 0, st>>>(w, N, N, idx, pc);
   CHD_LAUNCHED();
+  if (Gfull) {
+    compact_kernel<<<T, 32, 0, st>>>(w, N, N, idx_rem, cnt_rem, 1);
+    CHD_LAUNCHED();
+    choose_list_kernel<<<T, 128, 0, st>>>(idx, pc, idx_rem, cnt_rem, N, 1, idx_sel, cnt_sel, down);
+    CHD_LAUNCHED();
+    idx = idx_sel;
+    pc = cnt_sel;
+  }
   {
     size_t total = (size_t)n * ldp;
     int blocks = (int)((total + 255) / 256);
@@ -327,13 +371,29 @@ int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, cons
   if (symm) {
     const int tb = (n + GT - 1) / GT;
     gram_kernel<true><<<dim3(tb * (tb + 1) / 2, T), 256, 0, st>>>(Xc, Xc, n, n, ldp, pc, K, ldk, *kd, P, pmode, Xr,
-                                                                 pc2);
+                                                                 pc2, Gfull, Gfull ? down : nullptr);
   } else {
     const int ti = (nq + GT - 1) / GT, tj = (n + GT - 1) / GT;
-    gram_kernel<false><<<dim3(ti * tj, T), 256, 0, st>>>(Xqc, Xc, nq, n, ldp, pc, K, ldk, *kd, nullptr, 0, Xr, pc2);
+    gram_kernel<false><<<dim3(ti * tj, T), 256, 0, st>>>(Xqc, Xc, nq, n, ldp, pc, K, ldk, *kd, nullptr, 0, Xr, pc2,
+                                                         nullptr, nullptr);
   }
   CHD_LAUNCHED();
   return CHD_OK;
+}
+
+// G = X X^T over ALL N variables (raw linear core, n x ldk), for the downdate mode; `ones` = N bytes of scratch
+int gram_full_core_launch(const Plan* pl, const double* X, double* G, int ldk, uint8_t* ones, void* ws,
+                          size_t ws_bytes, cudaStream_t st) {
+  CHD_CUDA(cudaMemsetAsync(ones, 1, (size_t)pl->N, st));
+  chd_kernel_desc raw = {};
+  raw.kind = CHD_KERNEL_RAW;
+  raw.scale = 1.0;
+  return gram_launch(pl, &raw, X, X, pl->n, ones, 1, G, ldk, ws, ws_bytes, st, nullptr, 0, nullptr, nullptr);
+}
+
+// bytes of the shared core + its mask, carved in front of a Gram workspace
+size_t gram_full_core_bytes(const Plan* pl) {
+  return align_up((size_t)pl->n * align_up(pl->n, 2) * sizeof(double), 256) + align_up((size_t)pl->N, 256);
 }
 
 }  // namespace chd
@@ -343,8 +403,24 @@ extern "C" int chd_gram(const chd_plan* plan, const chd_kernel_desc* kd, const d
                         void* stream) {
   const chd::Plan* pl = (const chd::Plan*)plan;
   if (!pl || !kd || !X || !Xq || !w || !K || T <= 0 || nq <= 0 || ldk < pl->n || (ldk & 1)) return CHD_EINVAL;
-  return chd::gram_launch(pl, kd, X, Xq, nq, w, T, K, ldk, workspace, workspace_bytes, (cudaStream_t)stream, nullptr,
-                          0, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  // train Gram of a batch (stage 1: every target lacks only itself and its impossible edges): one shared core
+  // G = X X^T, then a rank-r downdate per target
+  const double* G = nullptr;
+  char* ws = (char*)workspace;
+  size_t left = workspace_bytes;
+  if (pl->gram_downdate && Xq == X && nq == pl->n && T >= 4 && ldk == (int)chd::align_up(pl->n, 2)) {
+    const size_t gb = chd::gram_full_core_bytes(pl);
+    if (left > gb) {
+      double* Gw = (double*)ws;
+      uint8_t* ones = (uint8_t*)(ws + chd::align_up((size_t)pl->n * ldk * sizeof(double), 256));
+      ws += gb; left -= gb;
+      const int rc = chd::gram_full_core_launch(pl, X, Gw, ldk, ones, ws, left, st);
+      if (rc) return rc;
+      G = Gw;
+    }
+  }
+  return chd::gram_launch(pl, kd, X, Xq, nq, w, T, K, ldk, ws, left, st, nullptr, 0, nullptr, G);
 }
 
 extern "C" int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, const double* X, const double* Xq,
@@ -360,7 +436,7 @@ extern "C" int chd_predict(const chd_plan* plan, const chd_kernel_desc* kd, cons
   size_t used = chd::align_up(cv.off, 256);
   // cross-Gram always takes the non-symmetric path: pass distinct pointer semantics via nq/Xq
   int rc = chd::gram_launch(pl, kd, X, Xq, nq, w, T, K, ldk, (char*)workspace + used, workspace_bytes - used,
-                            (cudaStream_t)stream, nullptr, 0, nullptr);
+                            (cudaStream_t)stream, nullptr, 0, nullptr, nullptr);
   if (rc) return rc;
   const int warps = 8;
   chd::predict_gemv_kernel<<<dim3((nq + warps - 1) / warps, T), warps * 32, 0, (cudaStream_t)stream>>>(

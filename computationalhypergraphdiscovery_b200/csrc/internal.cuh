@@ -51,7 +51,11 @@ int band_solve_launch(const Plan* pl, const double* bandS, double* Lg, const dou
 int gram_workspace(const Plan* pl, int T, int nq, size_t* bytes);
 int gram_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const double* Xq, int nq,
                 const uint8_t* w, int T, double* K, int ldk, void* ws, size_t ws_bytes, cudaStream_t st,
-                double* P, int pmode, const uint8_t* wrem);
+                double* P, int pmode, const uint8_t* wrem, const double* Gfull = nullptr);
+// shared linear core of the full variable set (downdate mode of the Gram, gram.cu)
+int gram_full_core_launch(const Plan* pl, const double* X, double* G, int ldk, uint8_t* ones, void* ws,
+                          size_t ws_bytes, cudaStream_t st);
+size_t gram_full_core_bytes(const Plan* pl);
 size_t act_workspace(const Plan* pl, int T);
 int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const int32_t* cluster_of,
                const uint8_t* w0, uint8_t* alive, const double* yb, const double* ga, int T, double* act,

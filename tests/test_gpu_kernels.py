@@ -250,3 +250,32 @@ def test_shared_gaussian_activations_match_oracle(clusters, N, T):
         ref = ochd.activations(spec, X, yb[t], ga[t], am, clusters)
         np.testing.assert_allclose(act[t], ref, rtol=1e-9, atol=1e-12)
         assert int(pruned[t]) == int(np.argmin(ref))
+
+
+@pytest.mark.parametrize("n,N", [(333, 11), (130, 70)])
+def test_gram_downdate_from_shared_core_matches_oracle(n, N):
+    """Batches of >= 4 targets take the downdate form  L = X X^T - X_r X_r^T  for the targets with fewer removed than
+    active variables (gram.cu); the others keep the direct form.  Same parity bar as the direct Gram, plus bitwise
+    symmetry."""
+    nat = _native()
+    X, _ = _data(n, N, 3)
+    plan = nat.Plan(n, N, N)
+    Xd = torch.from_numpy(X).to(plan.device)
+    rng = np.random.default_rng(4)
+    T = 7
+    w = np.ones((T, N), dtype=np.uint8)
+    w[0, 0] = 0                                      # stage-1 like: one removed
+    w[1, rng.choice(N, size=N // 4, replace=False)] = 0
+    w[2] = (rng.random(N) < 0.5)
+    w[3] = (rng.random(N) < 0.2)                     # mostly removed: direct form
+    w[4] = 0
+    w[4, 1] = 1
+    w[5] = 1                                         # nothing removed
+    w[6, N - 1] = 0
+    for spec in SPECS:
+        K = plan.gram(_desc(nat, spec), Xd, torch.from_numpy(w).to(plan.device)).cpu().numpy()[:, :, :n]
+        for t in range(T):
+            ref = okern.gram(spec, X, X, w[t].astype(float))
+            err = np.abs(K[t] - ref).max() / np.abs(ref).max()
+            assert err < 5e-14, (spec, t, err)
+            assert np.array_equal(K[t], K[t].T)
