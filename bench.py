@@ -599,7 +599,11 @@ def build_roofline(args, plan, prof_main, ms, n_mats, Tb, peak_tf, peak_src, hbm
         NBW = _native.BAND
         ms_list = [n - p * NBW for p in range(0, (n - 2) // NBW + 1) if n - p * NBW >= 2]
         ms_list = [n] + [m for m in ms_list[1:]]          # panel 0 is H_{-1} on the full matrix
-        gemm_flops = sum(2.0 * m * m * NBW for m in ms_list)   # per kernel, per matrix
+        gemm_flops = sum(2.0 * m * m * NBW for m in ms_list)   # symm, per matrix: every panel slot on its trailing block
+        # trailing update: once per group of two slots, on the trailing block of the group's LAST slot, K = 2 NB per slot
+        upd_flops = sum(2.0 * ms_list[min(g + 1, len(ms_list) - 1)] ** 2 * NBW * min(2, len(ms_list) - g)
+                        for g in range(0, len(ms_list), 2))
+        flops_of = {"symm": gemm_flops, "syr2k": upd_flops}
         kern_stats = {}
         for kname in ("symm", "syr2k", "panel_qr", "wform", "chase", "band_solve", "backtransform"):
             if kname in prof_main:
@@ -607,39 +611,52 @@ def build_roofline(args, plan, prof_main, ms, n_mats, Tb, peak_tf, peak_src, hbm
                 kern_stats[kname] = {"ms": kms, "launches": kcnt, "share_of_step": kms / ms}
         dom = max(("symm", "syr2k"), key=lambda k: prof_main.get(k, (0.0, 0))[0])
         dms, dcnt = prof_main.get(dom, (0.0, 1))
-        achieved_tf = gemm_flops * n_mats / (dms * 1e-3) / 1e12 if dms else 0.0
-        # algorithmic bytes: symm reads the lower triangle twice (tile + its transpose), syr2k reads + writes it once
-        alg_bytes = sum(8.0 * m * m for m in ms_list) * n_mats
+        achieved_tf = flops_of[dom] * n_mats / (dms * 1e-3) / 1e12 if dms else 0.0
+        # algorithmic bytes from HBM: symm reads the lower triangle once per panel (4 m^2 B: the transposed use of every
+        # block is the paired CTA's L2 hit); the trailing update reads + writes it once per group of two panels
+        # (8 m^2 B per group = 4 m^2 B per panel)
+        alg_bytes = sum(4.0 * m * m for m in ms_list) * n_mats
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "stage1_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_stage1_traffic.json")))
             per_matrix = tr.get(f"{dom}_n{n}_per_matrix")
             traffic = per_matrix * n_mats / max(dcnt, 1) if per_matrix else None
         except Exception:  # noqa: BLE001
             pass
         stage1_ms = sum(prof_main.get(k, (0.0, 0))[0] for k in ("symm", "syr2k", "panel_qr", "wform"))
-        kfull = {"symm": "symm_kernel", "syr2k": "syr2k_row_kernel"}[dom]
-        return {"kernel": f"{kfull} (dense->band stage of the two-stage reduction, FP64 DMMA m8n8k4, "
-                          f"batched over {Tb} targets per launch)",
+        per_gemm = {}
+        for k in ("symm", "syr2k"):
+            kms = prof_main.get(k, (0.0, 0))[0]
+            if kms:
+                tf = flops_of[k] * n_mats / (kms * 1e-3) / 1e12
+                per_gemm[k] = {"achieved_tflops": tf, "frac_of_dmma_peak": tf / peak_tf if peak_tf else None}
+        kfull = {"symm": "symm_tma_kernel (Y = A22 V, paired block schedule)",
+                 "syr2k": "syr2k_tma_kernel (trailing update of a group of two panels, K = 128)"}[dom]
+        return {"kernel": f"{kfull}: TMA tensor-map tiles + mbarrier ring + FP64 DMMA m8n8k4, dense->band stage of "
+                          f"the two-stage reduction, batched over {Tb} targets per launch",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes of one capture (profiles/stage1_traffic.json), scaled per launch",
+                "traffic_source": "ncu dram__bytes of one capture per kernel (profiles/r02_stage1_traffic.json), "
+                                  "scaled over the panels by the kernels' m^2 law, per launch",
                 "peak_source": peak_src,
-                "flops_per_launch": gemm_flops * n_mats / max(dcnt, 1),
+                "flops_per_launch": flops_of[dom] * n_mats / max(dcnt, 1),
                 "avg_launch_ms": dms / max(dcnt, 1), "launches_timed": dcnt, "share_of_step": dms / ms,
+                "gemm_kernels": per_gemm,
                 "stage1": {"credited_flops_per_matrix": credited_flops_tridiag(n),
                            "achieved_tflops": credited_flops_tridiag(n) * n_mats / (stage1_ms * 1e-3) / 1e12
                            if stage1_ms else None,
                            "frac_of_dmma_peak": (credited_flops_tridiag(n) * n_mats / (stage1_ms * 1e-3) / 1e12 /
                                                  peak_tf) if stage1_ms and peak_tf else None,
                            "ms_per_matrix": stage1_ms / n_mats,
-                           "note": "symm + syr2k + panel QR + W formation, credited 4/3 n^3 (SURVEY 8d)"},
+                           "note": "symm + trailing update + panel QR (+ thin update) + partial sums / small matrices / "
+                                   "W / Z block, credited 4/3 n^3 (SURVEY 8d)"},
                 "kernels": kern_stats,
                 "hbm_view": {"bound": "hbm", "achieved": alg_bytes / (dms * 1e-3) / 1e9 if dms else None,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (dms * 1e-3) / 1e9 / hbm_peak if dms else None,
-                             "note": "8 m^2 B per panel and matrix for either GEMM kernel (symm: lower triangle "
-                                     "read as tile and as transposed tile; syr2k: read + write)"}}
+                             "note": "4 m^2 B per panel and matrix for either GEMM kernel (symm: lower triangle read "
+                                     "once, the transposed use is an L2 hit; trailing update: read + write once per "
+                                     "two panels)"}}
     mats_per_launch = n_mats / max(tri_launches, 1)
     dur = tri_ms * 1e-3 / max(tri_launches, 1)
     achieved_tf = credited_flops_tridiag(n) * n_mats / (tri_ms * 1e-3) / 1e12

@@ -364,6 +364,184 @@ __global__ void __launch_bounds__(CC_THREADS, 10) chase_cta_kernel(ChaseArgs a) 
   }
 }
 
+// ---- CTA-per-sweep kernel, second formulation (default): the same arithmetic as chase_cta_kernel with 5 block barriers
+// per hop instead of 11, no memory fence besides the release store, and the progress flag of hop h published after
+// the first barrier of hop h + 1 (its stores are then ordered by that barrier) -- ncu showed the first formulation
+// stalled on barriers (8.8 warps per issued instruction) and on the fence, not on arithmetic:
+//   #1 blocks staged in shared memory      #2 partial products D v and S v (both at once)
+//   #3 w of the two-sided update           #4 D, S H updated, next reflector from column 0 (every warp computes it from
+//                                             the pre-update column, so nobody waits for the owner of column 0)
+//   #5 partial products v2^T S;  the left update and the stores of S then run from registers.
+constexpr int C2_SMEM_DOUBLES = 2 * CB * CS_ + 5 * CB + 2 * CC_PARTS * CB;
+
+__global__ void __launch_bounds__(CC_THREADS, 10) chase_cta2_kernel(ChaseArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, part = tid >> 5;
+  const int t = blockIdx.y, n = a.n;
+  double* bw = a.bandW + (size_t)t * n * CLD;
+  int* prog = a.prog + (size_t)t * n;
+  __shared__ int s_j, s_ok, s_seen;
+  double* D = smem;                    // CB x CS_
+  double* S = D + CB * CS_;            // CB x CS_
+  double* vs = S + CB * CS_;           // CB
+  double* ws = vs + CB;                // CB
+  double* v2s = ws + CB;               // CB
+  double* col0 = v2s + CB;             // CB   column 0 of S after both updates
+  double* spare = col0 + CB;           // CB
+  double* red = spare + CB;            // CC_PARTS x CB
+  double* red2 = red + CC_PARTS * CB;  // CC_PARTS x CB
+  (void)spare;
+  const int c0 = part * CC_W;          // this thread's column slice (row = lane) / row slice (column = lane)
+
+  while (true) {
+    __syncthreads();                   // s_j of the previous sweep has been read by everybody
+    if (tid == 0) { s_j = atomicAdd(a.ticket + t, 1); s_ok = 1; }
+    __syncthreads();
+    const int j = s_j;
+    if (j > n - 3) break;
+    int lo = j + 1, hi = min(j + CB, n - 1);
+    int len = hi - lo + 1;
+    int h = 0;
+    int pending = 0;                   // hops finished but not yet published
+    int seen = (j == 0) ? CH_DONE : 0;
+    auto wait_prev = [&](int need) -> bool {
+      if (seen >= need) return true;
+      __syncthreads();                 // the stores of the finished hops are ordered before the flag below
+      if (tid == 0) {
+        if (pending) st_release(prog + j, pending);
+        unsigned long long spins = 0;
+        int v;
+        while ((v = ld_acquire(prog + j - 1)) < need)
+          if (++spins > CH_SPIN_LIMIT) { s_ok = 0; atomicExch(a.err, 1); break; }
+        s_seen = v;
+      }
+      pending = 0;
+      __syncthreads();
+      seen = s_seen;
+      return s_ok != 0;
+    };
+    bool alive = wait_prev(2);
+    if (!alive) { if (tid == 0) st_release(prog + j, CH_DONE); break; }
+    // first reflector of the sweep: column j, rows lo..hi (every warp computes it: lane = row)
+    double v, tau, beta;
+    {
+      const double x = (lane < len) ? __ldcg(bw + (size_t)(lo + lane) * CLD + (lane + 1)) : 0.0;
+      warp_reflector(x, lane, len, v, tau, beta);
+      if (part == 0 && lane < len) __stcg(bw + (size_t)(lo + lane) * CLD + (lane + 1), (lane == 0) ? beta : 0.0);
+    }
+    while (true) {
+      const int lo2 = hi + 1, hi2 = min(hi + CB, n - 1);
+      const int len2 = hi2 - lo2 + 1;
+      const int off = lo2 - lo;
+      const bool has_s = len2 > 0, has_refl = len2 >= 2;
+      // ---------------- loads: warp `part` fetches rows c0 .. c0 + CC_W - 1 of both blocks
+      double dr[CC_W], sr[CC_W];
+#pragma unroll
+      for (int i = 0; i < CC_W; ++i) {
+        const int l = c0 + i;
+        dr[i] = (l < len && lane <= l) ? __ldcg(bw + (size_t)(lo + l) * CLD + lane) : 0.0;
+        sr[i] = (l < len2 && lane < len) ? __ldcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane)) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < CC_W; ++i) {
+        const int l = c0 + i;
+        if (lane <= l) {
+          D[l * CS_ + (l - lane)] = dr[i];
+          D[(l - lane) * CS_ + l] = dr[i];
+        }
+        S[l * CS_ + lane] = sr[i];
+      }
+      if (part == 0) vs[lane] = v;
+      __syncthreads();                                                       // #1
+      if (pending && tid == 0) st_release(prog + j, pending);                // hops up to `pending` are complete
+      pending = 0;
+      // ---------------- partial products over this thread's columns: D v and S v
+      {
+        double pp = 0.0, uu = 0.0;
+#pragma unroll
+        for (int c = 0; c < CC_W; ++c) {
+          const double vc = vs[c0 + c];
+          pp = fma(D[lane * CS_ + c0 + c], vc, pp);
+          uu = fma(S[lane * CS_ + c0 + c], vc, uu);
+        }
+        red[part * CB + lane] = pp;
+        red2[part * CB + lane] = uu;
+      }
+      __syncthreads();                                                       // #2
+      double p = 0.0, u = 0.0;
+#pragma unroll
+      for (int q = 0; q < CC_PARTS; ++q) { p += red[q * CB + lane]; u += red2[q * CB + lane]; }
+      p *= tau;
+      u *= tau;
+      const double al = -0.5 * tau * warp_sum(p * v);
+      const double wv = p + al * v;
+      if (part == 0) ws[lane] = wv;
+      __syncthreads();                                                       // #3
+      // ---------------- D <- H D H and S <- S H on this thread's row slice; column 0 of S is replaced below, so it is
+      // left alone here (every warp still reads its pre-update value)
+      double v2 = 0.0, tau2 = 0.0;
+      {
+        const double x0 = S[lane * CS_] - u * vs[0];       // column 0 after S H
+#pragma unroll
+        for (int c = 0; c < CC_W; ++c) {
+          const double vc = vs[c0 + c];
+          D[lane * CS_ + c0 + c] -= v * ws[c0 + c] + wv * vc;
+          if (c0 + c != 0) S[lane * CS_ + c0 + c] -= u * vc;
+        }
+        double nc0 = x0;
+        if (has_refl) {
+          double beta2;
+          warp_reflector(x0, lane, len2, v2, tau2, beta2);   // identical in every warp
+          nc0 = (lane == 0) ? beta2 : 0.0;
+        }
+        if (part == 0) { v2s[lane] = v2; col0[lane] = nc0; }
+      }
+      __syncthreads();                                                       // #4
+      // ---------------- store D (rows c0 .. of this warp, coalesced) ; partial products v2^T S of this thread's rows
+#pragma unroll
+      for (int i = 0; i < CC_W; ++i) {
+        const int l = c0 + i;
+        if (l < len && lane <= l) __stcg(bw + (size_t)(lo + l) * CLD + lane, D[l * CS_ + (l - lane)]);
+      }
+      double sv[CC_W];
+      {
+        double zz = 0.0;
+#pragma unroll
+        for (int i = 0; i < CC_W; ++i) {
+          sv[i] = S[(c0 + i) * CS_ + lane];
+          zz = fma(v2s[c0 + i], sv[i], zz);
+        }
+        red[part * CB + lane] = zz;
+      }
+      __syncthreads();                                                       // #5
+      if (has_s) {
+        double z = 0.0;
+#pragma unroll
+        for (int q = 0; q < CC_PARTS; ++q) z += red[q * CB + lane];
+        z = (has_refl && lane >= 1) ? z * tau2 : 0.0;
+#pragma unroll
+        for (int i = 0; i < CC_W; ++i) {
+          const int l = c0 + i;
+          const double val = (lane == 0) ? col0[l] : sv[i] - v2s[l] * z;
+          if (l < len2 && lane < len) __stcg(bw + (size_t)(lo2 + l) * CLD + (off + l - lane), val);
+        }
+      }
+      ++h;
+      if (!has_refl) {
+        // last hop of the sweep: publish DONE once everybody's stores are issued
+        __syncthreads();
+        if (tid == 0) st_release(prog + j, CH_DONE);
+        break;
+      }
+      pending = h;                     // published after barrier #1 of the next hop (or by wait_prev)
+      v = v2; tau = tau2; lo = lo2; hi = hi2; len = len2;
+      alive = wait_prev(h + 2);
+      if (!alive) { if (tid == 0) st_release(prog + j, CH_DONE); break; }
+    }
+    if (!alive) break;
+  }
+}
+
 __global__ void chase_extract_kernel(const double* __restrict__ bandW, int n, const int* __restrict__ err,
                                      double* __restrict__ d, double* __restrict__ e) {
   const int t = blockIdx.y;
@@ -381,15 +559,20 @@ size_t chase_prog_ints(const Plan* pl, int T) { return (size_t)T * pl->n + (size
 size_t chase_workspace(const Plan* pl, int T) { return align_up(chase_prog_ints(pl, T) * sizeof(int), 256) + 256; }
 
 int chase_device_init(Plan* pl) {
-  const int variant = getenv("CHD_CHASE") ? atoi(getenv("CHD_CHASE")) : 1;   // 0: one warp per sweep
+  // 2: CTA per sweep, 5 barriers per hop (default); 1: CTA per sweep, first formulation; 0: one warp per sweep
+  const int variant = getenv("CHD_CHASE") ? atoi(getenv("CHD_CHASE")) : 2;
   pl->chase_variant = variant;
   const size_t smem = variant == 0 ? (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double)
+                    : variant == 2 ? (size_t)C2_SMEM_DOUBLES * sizeof(double)
                                    : (size_t)CC_SMEM_DOUBLES * sizeof(double);
   const int threads = variant == 0 ? CH_WARPS * 32 : CC_THREADS;
   int nb = 0;
   if (variant == 0) {
     CHD_CUDA(cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_kernel, threads, smem));
+  } else if (variant == 2) {
+    CHD_CUDA(cudaFuncSetAttribute(chase_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_cta2_kernel, threads, smem));
   } else {
     CHD_CUDA(cudaFuncSetAttribute(chase_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CHD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, chase_cta_kernel, threads, smem));
@@ -411,6 +594,7 @@ int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e,
   const int n = pl->n;
   const int variant = pl->chase_variant;
   const size_t smem = variant == 0 ? (size_t)CH_WARPS * (2 * CB * CS_ + 3 * CB) * sizeof(double)
+                    : variant == 2 ? (size_t)C2_SMEM_DOUBLES * sizeof(double)
                                    : (size_t)CC_SMEM_DOUBLES * sizeof(double);
   const int threads = variant == 0 ? CH_WARPS * 32 : CC_THREADS;
   const int sweeps_per_cta = variant == 0 ? CH_WARPS : 1;
@@ -444,6 +628,7 @@ int chase_launch(const Plan* pl, double* bandW, int* prog, double* d, double* e,
       a.bandW = bandW + (size_t)t0 * n * CLD; a.prog = prog + (size_t)t0 * n; a.ticket = ticket + t0; a.err = err;
       a.n = n;
       if (variant == 0) chase_kernel<<<dim3(per, cnt), threads, smem, st>>>(a);
+      else if (variant == 2) chase_cta2_kernel<<<dim3(per, cnt), threads, smem, st>>>(a);
       else chase_cta_kernel<<<dim3(per, cnt), threads, smem, st>>>(a);
       CHD_LAUNCHED();
     }
