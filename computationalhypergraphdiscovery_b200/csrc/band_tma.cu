@@ -19,25 +19,25 @@ namespace chd {
 
 namespace {
 
-constexpr int TM_BM = 128;           // rows of the CTA's block
 constexpr int TM_BN = 16;            // tile columns (one 16-column box)
-constexpr int TM_NST = 3;            // ring depth
-constexpr int TM_CONS_WARPS = 8;
-constexpr int TM_THREADS = 32 * (1 + TM_CONS_WARPS);
 constexpr int TM_CH = 32;            // tiles per CTA (512 columns)
 constexpr int BOX_ROWS = 16;         // every box is 16 columns x 16 rows (2 KB)
 constexpr int BOX_BYTES = 16 * BOX_ROWS * 8;
 
-// shared memory (bytes): Z_I: KB boxes-columns of 128 rows; per stage: Z'_J (KB box-columns of 16 rows) + A tile
-template <int G> struct TmCfg {
+// BM = rows of the CTA's block (128: one CTA per SM with a 3-stage ring; 64: two CTAs per SM with 2-stage rings, so that
+// the Z_I load and the pipeline fill of one CTA overlap with the other's main loop), G = panels of the group
+template <int G, int BM> struct TmCfg {
+  static constexpr int NST = (BM == 128) ? 3 : 2;       // ring depth
+  static constexpr int CONS_WARPS = BM / 16;
+  static constexpr int THREADS = 32 * (1 + CONS_WARPS);
   static constexpr int KT = 2 * G * NB;                 // K of the update (64 or 128)
   static constexpr int KB = KT / 16;                    // 16-column boxes along K
-  static constexpr int ZI_BYTES = KB * TM_BM * 128;     // 64 / 128 KB
-  static constexpr int ZJ_BYTES = KB * TM_BN * 128;     // 8 / 16 KB
-  static constexpr int A_BYTES = TM_BM * 128;           // 16 KB
+  static constexpr int ZI_BYTES = KB * BM * 128;        // Z_I: KB box-columns of BM rows
+  static constexpr int ZJ_BYTES = KB * TM_BN * 128;     // Z'_J: KB box-columns of 16 rows
+  static constexpr int A_BYTES = BM * 128;              // A tile
   static constexpr int STAGE_BYTES = ZJ_BYTES + A_BYTES;
-  static constexpr int BAR_OFF = ZI_BYTES + TM_NST * STAGE_BYTES;
-  static constexpr int SMEM = BAR_OFF + 64 + 1024;      // + barriers + slack for the 1024-byte alignment
+  static constexpr int BAR_OFF = ZI_BYTES + NST * STAGE_BYTES;
+  static constexpr int SMEM = BAR_OFF + 64;             // the dynamic shared array is declared 1024-byte aligned
 };
 
 struct TmArgs {
@@ -45,15 +45,14 @@ struct TmArgs {
   int n, r0;
 };
 
-template <int G>
-__global__ void __launch_bounds__(TM_THREADS, 1)
+template <int G, int BM>
+__global__ void __launch_bounds__(TmCfg<G, BM>::THREADS, BM == 128 ? 1 : 2)
 syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapV,
                  const __grid_constant__ CUtensorMap mapW, TmArgs a) {
-  using C = TmCfg<G>;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment (swizzle period) by pointer arithmetic on the shared array, so that the compiler keeps the
-  // shared address space (LDS, not generic LD)
-  uint8_t* sm = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  using C = TmCfg<G, BM>;
+  constexpr int TM_NST = C::NST;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // swizzle period: box stacks start on 1024-byte boundaries
+  uint8_t* sm = smem_raw;
   uint8_t* zi = sm;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);
   uint64_t* full = bars;                 // TM_NST
@@ -62,9 +61,9 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   const int t = blockIdx.z;
   const int n = a.n, r0 = a.r0;
-  const int i0 = r0 + TM_BM * blockIdx.y;
-  // 16-column tiles of this block row that touch the lower triangle: j0 = r0 + 16 jt <= i0 + 127, j0 < n
-  const int njt = min((i0 + TM_BM - r0) / TM_BN, (n - r0 + TM_BN - 1) / TM_BN);
+  const int i0 = r0 + BM * blockIdx.y;
+  // 16-column tiles of this block row that touch the lower triangle: j0 = r0 + 16 jt <= i0 + BM - 1, j0 < n
+  const int njt = min((i0 + BM - r0) / TM_BN, (n - r0 + TM_BN - 1) / TM_BN);
   const int jt_lo = TM_CH * blockIdx.x, jt_hi = min(njt, jt_lo + TM_CH);
   if (jt_lo >= jt_hi) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -72,7 +71,7 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (tid == 0) {
     for (int s = 0; s < TM_NST; ++s) {
       tma::mbar_init(full + s, 1);
-      tma::mbar_init(empty + s, TM_CONS_WARPS);
+      tma::mbar_init(empty + s, C::CONS_WARPS);
     }
     tma::mbar_init(zi_full, 1);
     tma::fence_mbar_init();
@@ -88,12 +87,12 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       tma::mbar_expect_tx(zi_full, C::ZI_BYTES);
     }
     __syncwarp();
-    // Z_I = [V_I | W_I]: box-column kb (16 K-columns) x 8 row boxes; lanes share the copies
-    for (int b = lane; b < C::KB * (TM_BM / BOX_ROWS); b += 32) {
-      const int kb = b / (TM_BM / BOX_ROWS), rb = b % (TM_BM / BOX_ROWS);
+    // Z_I = [V_I | W_I]: box-column kb (16 K-columns) x BM / 16 row boxes; lanes share the copies
+    for (int b = lane; b < C::KB * (BM / BOX_ROWS); b += 32) {
+      const int kb = b / (BM / BOX_ROWS), rb = b % (BM / BOX_ROWS);
       const bool fromV = kb < C::KB / 2;
       const int col = 16 * (fromV ? kb : kb - C::KB / 2);
-      tma::load_box(zi + kb * (TM_BM * 128) + rb * BOX_BYTES, fromV ? &mapV : &mapW, col, i0 + BOX_ROWS * rb, t,
+      tma::load_box(zi + kb * (BM * 128) + rb * BOX_BYTES, fromV ? &mapV : &mapW, col, i0 + BOX_ROWS * rb, t,
                     zi_full);
     }
     for (int jt = jt_lo; jt < jt_hi; ++jt) {
@@ -103,8 +102,8 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int j0 = r0 + TM_BN * jt;
       if (lane == 0) tma::mbar_expect_tx(full + s, C::STAGE_BYTES);
       __syncwarp();
-      // Z'_J = [W_J | V_J]: KB boxes of 16 rows; the A tile: 8 boxes of 16 rows
-      for (int b = lane; b < C::KB + TM_BM / BOX_ROWS; b += 32) {
+      // Z'_J = [W_J | V_J]: KB boxes of 16 rows; the A tile: BM / 16 boxes of 16 rows
+      for (int b = lane; b < C::KB + BM / BOX_ROWS; b += 32) {
         if (b < C::KB) {
           const bool fromW = b < C::KB / 2;
           const int col = 16 * (fromW ? b : b - C::KB / 2);
@@ -147,7 +146,7 @@ syr2k_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
 #pragma unroll
     for (int kb = 0; kb < C::KB; ++kb) {
-      const uint8_t* zik = zi_row + kb * (TM_BM * 128);
+      const uint8_t* zik = zi_row + kb * (BM * 128);
       const uint8_t* zjk = zj_row + kb * BOX_BYTES;
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -200,15 +199,15 @@ constexpr int SM_STAGE = SM_A_BYTES + SM_V_BYTES;
 constexpr int SM_THREADS = 32 * (1 + 8);
 // SM_NST stages per CTA: 4 with one CTA per SM, 2 with two CTAs per SM (16 consumer warps per SM, the epilogue and the
 // pipeline fill of one CTA overlap with the other's main loop)
-template <int SM_NST> constexpr int symm_tma_smem() { return SM_NST * SM_STAGE + 64 + 1024; }
+template <int SM_NST> constexpr int symm_tma_smem() { return SM_NST * SM_STAGE + 64; }
 
 template <int SM_NST>
 __global__ void __launch_bounds__(SM_THREADS, SM_NST == 2 ? 2 : 1)
 symm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAt,
                 const __grid_constant__ CUtensorMap mapV, SymmArgs a) {
   constexpr int SM_BAR_OFF = SM_NST * SM_STAGE;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = smem_raw + ((1024u - (tma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = smem_raw;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BAR_OFF);
   uint64_t* full = bars;
   uint64_t* empty = bars + SM_NST;
@@ -337,8 +336,16 @@ int band_tma_device_init(Plan* pl) {
   pl->syr2k_tma = 1;
   if (const char* e = getenv("CHD_SYR2K_TMA")) pl->syr2k_tma = atoi(e) ? 1 : 0;
   if (!tma::encode_fn()) pl->syr2k_tma = 0;
-  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<1>::SMEM));
-  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<2>::SMEM));
+  pl->syr2k_tma_ctas = 2;
+  if (const char* e = getenv("CHD_SYR2K_TMA_CTAS")) pl->syr2k_tma_ctas = atoi(e) == 1 ? 1 : 2;
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TmCfg<1, 128>::SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TmCfg<2, 128>::SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TmCfg<1, 64>::SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(syr2k_tma_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TmCfg<2, 64>::SMEM));
   pl->symm_tma = 1;
   if (const char* e = getenv("CHD_SYMM_TMA")) pl->symm_tma = atoi(e) ? 1 : 0;
   if (!tma::encode_fn()) pl->symm_tma = 0;
@@ -378,9 +385,19 @@ int syr2k_tma_launch(const Plan* pl, double* K, int ldk, int T, int r0, int G, c
   TmArgs a;
   a.A = K; a.strideA = (size_t)n * ldk; a.ldk = ldk; a.n = n; a.r0 = r0;
   const int ntile = (m + TM_BN - 1) / TM_BN;
-  const dim3 grid((ntile + TM_CH - 1) / TM_CH, (m + TM_BM - 1) / TM_BM, T);
-  if (G == 1) syr2k_tma_kernel<1><<<grid, TM_THREADS, TmCfg<1>::SMEM, st>>>(mapA, mapV, mapW, a);
-  else syr2k_tma_kernel<2><<<grid, TM_THREADS, TmCfg<2>::SMEM, st>>>(mapA, mapV, mapW, a);
+  if (pl->syr2k_tma_ctas == 2) {
+    const dim3 grid((ntile + TM_CH - 1) / TM_CH, (m + 63) / 64, T);
+    if (G == 1)
+      syr2k_tma_kernel<1, 64><<<grid, TmCfg<1, 64>::THREADS, TmCfg<1, 64>::SMEM, st>>>(mapA, mapV, mapW, a);
+    else
+      syr2k_tma_kernel<2, 64><<<grid, TmCfg<2, 64>::THREADS, TmCfg<2, 64>::SMEM, st>>>(mapA, mapV, mapW, a);
+  } else {
+    const dim3 grid((ntile + TM_CH - 1) / TM_CH, (m + 127) / 128, T);
+    if (G == 1)
+      syr2k_tma_kernel<1, 128><<<grid, TmCfg<1, 128>::THREADS, TmCfg<1, 128>::SMEM, st>>>(mapA, mapV, mapW, a);
+    else
+      syr2k_tma_kernel<2, 128><<<grid, TmCfg<2, 128>::THREADS, TmCfg<2, 128>::SMEM, st>>>(mapA, mapV, mapW, a);
+  }
   CHD_LAUNCHED();
   return CHD_OK;
 }

@@ -51,6 +51,7 @@ struct Plan {
   int band_kd;             // panels per deferred trailing update of the dense -> band stage (1 or 2)
   int symm_tma_ctas;       // CTAs per SM of the TMA symm kernel (2: two 2-stage rings, 1: one 4-stage ring)
   int symm_tma;            // 1: TMA + mbarrier warp-specialised Y = A22 V with the paired block schedule
+  int syr2k_tma_ctas;      // CTAs per SM of the TMA trailing update (2: 64-row blocks, 1: 128-row blocks)
   int syr2k_tma;           // 1: TMA + mbarrier warp-specialised trailing update (band_tma.cu), 0: cp.async kernel
 };
 
