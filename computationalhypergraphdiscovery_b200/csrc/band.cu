@@ -630,6 +630,45 @@ __global__ void __launch_bounds__(256) symm_partials_kernel(SymmArgs a) {
   const int t = blockIdx.y, bx = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = a.n, i0 = a.r0 + SY_BM * bx;
   const double* V = a.V + (size_t)t * n * LDV;
+  // blockIdx.z = 1: the Z-block product V_I^T B_I only (its own CTA, so that its long load chain overlaps with the
+  // Y / Gram half of the same row block)
+  if (blockIdx.z == 1) {
+    if (!(a.Bq && a.nz > 0)) return;
+    for (int e = tid; e < SY_BM * NB; e += 256) {
+      const int rl = e / NB, c = e % NB;
+      Vs[rl * (NB + 1) + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
+    }
+    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
+    const int z = tid & 127, c1g = tid >> 7;   // 2 groups of 16 reflector columns
+    double zp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) zp[u] = 0.0;
+    // batches of 16 rows, the next batch's loads in flight while the current one is multiplied
+    double bv[16], nx[16];
+    auto fetch = [&](int rb, double (&dst)[16]) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        dst[q] = (z < a.nz && i0 + rb + q < n) ? Bq[(size_t)(i0 + rb + q) * a.ldb + z] : 0.0;
+    };
+    fetch(0, bv);
+    __syncthreads();
+#pragma unroll 1
+    for (int rb = 0; rb < SY_BM; rb += 16) {
+      if (rb + 16 < SY_BM) fetch(rb + 16, nx);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[(rb + q) * (NB + 1) + 16 * c1g + u], bv[q], zp[u]);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) bv[q] = nx[q];
+    }
+    if (z < a.nz) {
+      double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
+    }
+    return;
+  }
   double* Y0 = a.Y + (size_t)t * n * NB;
   for (int e = tid; e < SY_BM * NB; e += 256) {
     const int rl = e / NB, c = e % NB;
@@ -645,6 +684,7 @@ __global__ void __launch_bounds__(256) symm_partials_kernel(SymmArgs a) {
   __syncthreads();
   {
     double mp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
     for (int rl = 0; rl < SY_BM; ++rl) {
       const double yv = Ys[rl * (NB + 1) + lane];
 #pragma unroll
@@ -665,6 +705,7 @@ __global__ void __launch_bounds__(256) symm_partials_kernel(SymmArgs a) {
       }
       __syncthreads();
       double gp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
       for (int rl = 0; rl < SY_BM; ++rl) {
         const double vv = Vs[rl * (NB + 1) + lane];
 #pragma unroll
@@ -674,29 +715,6 @@ __global__ void __launch_bounds__(256) symm_partials_kernel(SymmArgs a) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) Gp[(wid + 8 * u) * NB + lane] = gp[u];
     }
-  }
-  if (a.Bq && a.nz > 0) {
-    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
-    const int z = tid & 127, c1g = tid >> 7;   // 2 groups of 16 reflector columns
-    double zp[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) zp[u] = 0.0;
-    if (z < a.nz) {
-      // batches of 8 rows: the 8 loads of a batch are in flight together (rows beyond n read as zero)
-#pragma unroll 1
-      for (int rb = 0; rb < SY_BM; rb += 8) {
-        double bv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bv[q] = (i0 + rb + q < n) ? Bq[(size_t)(i0 + rb + q) * a.ldb + z] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-#pragma unroll
-          for (int u = 0; u < 16; ++u) zp[u] = fma(Vs[(rb + q) * (NB + 1) + 16 * c1g + u], bv[q], zp[u]);
-      }
-    }
-    double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) Zp[(16 * c1g + u) * SY_ZW + z] = zp[u];
   }
 }
 constexpr size_t SP_SMEM = (size_t)2 * SY_BM * (NB + 1) * sizeof(double);
@@ -920,6 +938,17 @@ __global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
   const double* TZ = a.TZ + (size_t)t * NB * SY_ZW;
   double* Bq = a.Bq + (size_t)t * n * a.ldb;
   const int z = tid & 127, hg = tid >> 7;
+  // batches of 8 rows (8 independent chains); the next batch's loads are in flight while the current one is multiplied,
+  // the first batch's while the operands are staged
+  double bv[8], nx[8];
+  auto fetch = [&](int ub, double (&dst)[8]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + hg + 2 * (ub + u);
+      dst[u] = (z < a.nz && i < n) ? Bq[(size_t)i * a.ldb + z] : 0.0;
+    }
+  };
+  fetch(0, bv);
   for (int e = tid; e < NB * SY_ZW; e += 256) TZs[e] = TZ[e];
   for (int e = tid; e < WF_BM * NB; e += 256) {
     const int rl = e / NB, c = e % NB;
@@ -927,16 +956,12 @@ __global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
   }
   __syncthreads();
   if (z >= a.nz) return;
-  // batches of 8 rows: all loads of a batch in flight before its first store, 8 independent chains
 #pragma unroll 1
   for (int ub = 0; ub < WF_BM / 2; ub += 8) {
-    double bv[8], sv[8];
+    if (ub + 8 < WF_BM / 2) fetch(ub + 8, nx);
+    double sv[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + hg + 2 * (ub + u);
-      bv[u] = (i < n) ? Bq[(size_t)i * a.ldb + z] : 0.0;
-      sv[u] = 0.0;
-    }
+    for (int u = 0; u < 8; ++u) sv[u] = 0.0;
 #pragma unroll 4
     for (int k = 0; k < NB; ++k) {
       const double zv = TZs[k * SY_ZW + z];
@@ -948,6 +973,8 @@ __global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
       const int i = i0 + hg + 2 * (ub + u);
       if (i < n) Bq[(size_t)i * a.ldb + z] = bv[u] - sv[u];
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) bv[u] = nx[u];
   }
 }
 
@@ -1388,7 +1415,7 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     if (!pl->symm_tma) CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
     if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
-    symm_partials_kernel<<<dim3(nblk, T), 256, SP_SMEM, st>>>(a);
+    symm_partials_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, SP_SMEM, st>>>(a);
     CHD_LAUNCHED();
   }
   {
