@@ -295,11 +295,19 @@ __global__ void __launch_bounds__(QR_THREADS) panel_qr_kernel(QrArgs a) {
 // tc) for all NB columns at once -- u[tc] is the squared norm the reflector needs, u[c > tc] gives v^T P, u[c < tc]
 // gives the Gram entries v_c . v_tc of the compact-WY factor -- together with row tc itself (from its owner).  The
 // row sums over the 32 rows of a warp use a transposing butterfly (31 shuffles for 32 columns).
+// TWO = true (panels with more than 16 x 512 rows, i.e. n > 8192): every thread owns a SECOND row (local rows
+// RG_THREADS ..) that lives in shared memory in natural column order; its products join the first row's before the
+// butterfly, so the exchanges per column stay the same and a 16-CTA cluster covers 16384 rows.  Second rows are never
+// pivot rows (their panel row index is >= RG_THREADS > NB).
 constexpr int RG_THREADS = 512;
 constexpr int RG_NW = RG_THREADS / 32;
 constexpr int RG_XW = 2 * NB;
+constexpr int RG_S2 = NB + 1;                                    // second-row stride: conflict-free column walks
+constexpr size_t RG_SMEM2 = (size_t)RG_THREADS * RG_S2 * sizeof(double);
 
+template <bool TWO>
 __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
+  extern __shared__ __align__(16) double rg_dyn[];               // TWO: RG_THREADS x RG_S2 second rows
   __shared__ __align__(16) double xch[2 * QR_MAXCS * RG_XW];
   __shared__ double red[RG_NW * NB];
   __shared__ double rowbuf[NB];
@@ -316,6 +324,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
   const int pr = g * a.RP + tid;
   const bool valid = (tid < a.RP) && (pr < m);
   double* rowg = A + (size_t)(r0 + (valid ? pr : 0)) * ldk + c0;
+  const int pr2 = pr + RG_THREADS;
+  const bool valid2 = TWO && (tid + RG_THREADS < a.RP) && (pr2 < m);
+  double* rowg2 = A + (size_t)(r0 + (valid2 ? pr2 : 0)) * ldk + c0;
+  double* PB = rg_dyn + tid * RG_S2;
 
   // the row lives in registers, ROTATED: after tc columns P[q] holds column (q + tc) mod NB, so that the column
   // being eliminated is always P[0] (static register indices inside a rolled loop: the fully unrolled variant
@@ -327,6 +339,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
     if (valid) v2 = *reinterpret_cast<const double2*>(rowg + c);
     P[c] = v2.x; P[c + 1] = v2.y;
   }
+  if (TWO) {
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) {
+      double2 v2 = make_double2(0.0, 0.0);
+      if (valid2) v2 = *reinterpret_cast<const double2*>(rowg2 + c);
+      PB[c] = v2.x; PB[c + 1] = v2.y;                            // an absent row is all zeros: it contributes nothing
+    }
+  }
   for (int e = tid; e < NB * QR_S; e += RG_THREADS) Gs[e] = 0.0;
   if (tid < NB) taus[tid] = 0.0;
 
@@ -337,13 +357,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
   for (int tc = 0; tc < NB; ++tc) {
     if (tc < nref) {
       const double x = (valid && pr > tc) ? P[0] : 0.0;
+      const double xb = TWO ? PB[tc] : 0.0;
       // ---- transposing butterfly: lane q ends up with sum over the warp's rows of x * P[q]
       double t16[16], t8[8], t4[4], t2[2], t1;
       {
         const bool hi = lane & 16;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const double a0 = x * P[c], a1 = x * P[c + 16];
+          double a0 = x * P[c], a1 = x * P[c + 16];
+          if (TWO) {                                             // P is rotated by tc, the second row is not
+            a0 = fma(xb, PB[(c + tc) & (NB - 1)], a0);
+            a1 = fma(xb, PB[(c + 16 + tc) & (NB - 1)], a1);
+          }
           const double keep = hi ? a1 : a0, send = hi ? a0 : a1;
           t16[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
@@ -429,14 +454,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
       }
       const double v = (!valid || pr < tc) ? 0.0 : ((pr == tc) ? 1.0 : x * scale);
       const double tv = tau * v;
+      const double vb = xb * scale, tvb = tau * vb;
 #pragma unroll
       for (int q = 1; q < NB; ++q) {
         if (q < NB - tc) {                        // columns c = tc + q > tc still to be eliminated
           const int c = tc + q;
-          P[q] = fma(-tv, fma(scale, tot[c], tot[NB + c]), P[q]);
+          const double f = fma(scale, tot[c], tot[NB + c]);
+          P[q] = fma(-tv, f, P[q]);
+          if (TWO) PB[c] = fma(-tvb, f, PB[c]);
         }
       }
       if (valid && pr >= tc) P[0] = (pr == tc) ? beta : v;
+      if (TWO) PB[tc] = vb;
       if (wid == 0) {
         if (lane < tc) Gs[lane * QR_S + tc] = fma(scale, tot[lane], tot[NB + lane]);
         if (lane == 0) taus[tc] = tau;
@@ -479,6 +508,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) panel_qr_reg_kernel(QrArgs a) {
       const double v0 = (c >= nref || pr < c) ? 0.0 : ((pr == c) ? 1.0 : P[c]);
       const double v1 = (c + 1 >= nref || pr < c + 1) ? 0.0 : ((pr == c + 1) ? 1.0 : P[c + 1]);
       *reinterpret_cast<double2*>(V + c) = make_double2(v0, v1);
+    }
+  }
+  if (TWO && valid2) {
+    double* V = a.V + (size_t)t * n * LDV + (size_t)(r0 + pr2) * LDV;
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) {
+      *reinterpret_cast<double2*>(rowg2 + c) = make_double2(PB[c], PB[c + 1]);
+      *reinterpret_cast<double2*>(V + c) = make_double2(c < nref ? PB[c] : 0.0, c + 1 < nref ? PB[c + 1] : 0.0);
     }
   }
   if (CS > 1) cluster.sync();
@@ -978,6 +1015,234 @@ __global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ the same small products on the FP64 tensor cores
+// The per-panel products of a row block with 32 x 32 / 32 x 100 matrices are GEMM-shaped (K = 32 or K = the block's
+// rows); as FMA loops they ran at 8 TFLOP/s with the FP64 pipe as the limiter (ncu: 27 % FP64 pipe, 15-25 % of the DRAM
+// bandwidth).  Here they are DMMA m8n8k4 chains: a warp owns 8 rows (wz_dmma_kernel) or a pair / a strip of 8 x 8
+// output tiles (partials_dmma_kernel); 32 x 32 operands sit in shared memory with stride NB + 4 and the Z operand with
+// stride SY_ZW + 4 (== 4 mod 16: the four k-rows of a B fragment land in different bank groups), row operands are
+// read from global memory straight into fragment position.  CHD_SMALL_DMMA=0 keeps the FMA kernels.
+constexpr int DM_S = NB + 4;
+constexpr int DM_SZ = SY_ZW + 4;
+constexpr size_t WZ_SMEM = (size_t)(4 * NB * DM_S + NB * DM_SZ) * sizeof(double);
+constexpr size_t PD_SMEM = (size_t)(2 * SY_BM * DM_S) * sizeof(double);
+
+// W = (Y - V_a G1 - W_a G2 - 1/2 V T^T M) T  and  B -= V (T^T V^T B)  for one 64-row block: warp w owns rows 8 w .. 8 w + 7
+__global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu, int has_z) {
+  extern __shared__ __align__(16) double smem[];
+  double* G1s = smem;                       // NB x DM_S each
+  double* G2s = G1s + NB * DM_S;
+  double* TMs = G2s + NB * DM_S;
+  double* Ts = TMs + NB * DM_S;
+  double* TZs = Ts + NB * DM_S;             // NB x DM_SZ
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = a.n, i = a.r0 + WF_BM * blockIdx.x + 8 * wid + fr;
+  const bool ok = i < n;
+  const bool corr = a.Gred != nullptr;
+  const double* V = a.V + (size_t)t * n * LDV;
+  {
+    const double* Tf = a.Tf + (size_t)t * a.tf_stride;
+    const double* TM = a.TM + (size_t)t * NB * NB;
+    const double* G = corr ? a.Gred + (size_t)t * 2 * NB * NB : nullptr;
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int o = (e / NB) * DM_S + (e % NB);
+      TMs[o] = TM[e];
+      Ts[o] = Tf[e];
+      if (corr) { G1s[o] = G[e]; G2s[o] = G[NB * NB + e]; }
+    }
+    if (has_z) {
+      const double* TZ = zu.TZ + (size_t)t * NB * SY_ZW;
+      for (int e = tid; e < NB * SY_ZW; e += 256) TZs[(e / SY_ZW) * DM_SZ + (e % SY_ZW)] = TZ[e];
+    }
+  }
+  // this lane's A fragments of V (row i, k = 4 s + fk) and the accumulators (row i, columns 8 y + 2 fk + {0, 1}) = Y
+  double av[NB / 4];
+#pragma unroll
+  for (int s_ = 0; s_ < NB / 4; ++s_) av[s_] = ok ? V[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+  double acc[NB / 8][2];
+#pragma unroll
+  for (int y = 0; y < NB / 8; ++y) {
+    acc[y][0] = 0.0; acc[y][1] = 0.0;
+    if (ok)
+      for (int sp = 0; sp < a.nsplit; ++sp) {
+        const double2 yv = *reinterpret_cast<const double2*>(a.Y + ((size_t)sp * a.T + t) * n * NB + (size_t)i * NB +
+                                                             8 * y + 2 * fk);
+        acc[y][0] += yv.x; acc[y][1] += yv.y;
+      }
+  }
+  double a1[NB / 4], a2[NB / 4];
+  if (corr) {
+    const double* Va = a.Va + (size_t)t * n * LDV;
+    const double* Wa = a.Wa + (size_t)t * n * LDV;
+#pragma unroll
+    for (int s_ = 0; s_ < NB / 4; ++s_) {
+      a1[s_] = ok ? -Va[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+      a2[s_] = ok ? -Wa[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (corr) {
+#pragma unroll
+    for (int s_ = 0; s_ < NB / 4; ++s_)
+#pragma unroll
+      for (int y = 0; y < NB / 8; ++y) {
+        dmma884(acc[y][0], acc[y][1], a1[s_], G1s[(4 * s_ + fk) * DM_S + 8 * y + fr]);   // Y -= V_a G1
+        dmma884(acc[y][0], acc[y][1], a2[s_], G2s[(4 * s_ + fk) * DM_S + 8 * y + fr]);   // Y -= W_a G2
+      }
+  }
+#pragma unroll
+  for (int s_ = 0; s_ < NB / 4; ++s_)
+#pragma unroll
+    for (int y = 0; y < NB / 8; ++y)
+      dmma884(acc[y][0], acc[y][1], -0.5 * av[s_], TMs[(4 * s_ + fk) * DM_S + 8 * y + fr]);   // X1 = Y - 1/2 V (T^T M)
+  // W = X1 T: the accumulator tile (columns 2 fk + {0, 1}) turned into A fragments (column fk) by two shuffles per k-step
+  double wv[NB / 8][2];
+#pragma unroll
+  for (int y = 0; y < NB / 8; ++y) { wv[y][0] = 0.0; wv[y][1] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < NB / 4; ++j) {
+    const int src = (lane & ~3) | (2 * (j & 1) + (fk >> 1));
+    const double v0 = __shfl_sync(0xffffffffu, acc[j >> 1][0], src);
+    const double v1 = __shfl_sync(0xffffffffu, acc[j >> 1][1], src);
+    const double xa = (fk & 1) ? v1 : v0;
+#pragma unroll
+    for (int y = 0; y < NB / 8; ++y) dmma884(wv[y][0], wv[y][1], xa, Ts[(4 * j + fk) * DM_S + 8 * y + fr]);
+  }
+  if (ok) {
+    double* W = a.W + (size_t)t * n * LDV + (size_t)i * LDV;
+#pragma unroll
+    for (int y = 0; y < NB / 8; ++y) *reinterpret_cast<double2*>(W + 8 * y + 2 * fk) = make_double2(wv[y][0], wv[y][1]);
+  }
+  if (has_z) {
+    // B[i][z] -= sum_k V[i][k] TZ[k][z]: 13 column tiles of 8 cover nz <= 104 (ldb and nz even: double2 accesses)
+    constexpr int ZT = 13;
+    double* Brow = zu.Bq + (size_t)t * n * zu.ldb + (size_t)i * zu.ldb;
+    double zc[ZT][2];
+#pragma unroll
+    for (int y = 0; y < ZT; ++y) {
+      const int c = 8 * y + 2 * fk;
+      double2 bv = make_double2(0.0, 0.0);
+      if (ok && c < zu.nz) bv = *reinterpret_cast<const double2*>(Brow + c);
+      zc[y][0] = bv.x; zc[y][1] = bv.y;
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < NB / 4; ++s_)
+#pragma unroll
+      for (int y = 0; y < ZT; ++y) dmma884(zc[y][0], zc[y][1], -av[s_], TZs[(4 * s_ + fk) * DM_SZ + 8 * y + fr]);
+    if (ok) {
+#pragma unroll
+      for (int y = 0; y < ZT; ++y) {
+        const int c = 8 * y + 2 * fk;
+        if (c < zu.nz) *reinterpret_cast<double2*>(Brow + c) = make_double2(zc[y][0], zc[y][1]);
+      }
+    }
+  }
+}
+
+// Partial products of a 128-row block (the DMMA form of symm_partials_kernel, same outputs):
+//   blockIdx.z = 0: sum of the split-K partials of Y, Mpart = V_I^T Y_I, Gpart = {W_a,I^T V_I, V_a,I^T V_I}
+//   blockIdx.z = 1: Zpart = V_I^T B_I
+__global__ void __launch_bounds__(256) partials_dmma_kernel(SymmArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* Ys = smem;                       // SY_BM x DM_S
+  double* Vs = Ys + SY_BM * DM_S;          // SY_BM x DM_S
+  const int t = blockIdx.y, bx = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = a.n, i0 = a.r0 + SY_BM * bx;
+  const double* V = a.V + (size_t)t * n * LDV;
+  const int x = wid & 3, yp = wid >> 2;    // output rows 8 x .. (a column block of V^T), half of the output columns
+  if (blockIdx.z == 1) {
+    if (!(a.Bq && a.nz > 0)) return;
+    for (int e = tid; e < SY_BM * NB; e += 256) {
+      const int rl = e / NB, c = e % NB;
+      Vs[rl * DM_S + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
+    }
+    __syncthreads();
+    // warp (x, yp): rows 8 x .. 8 x + 7 of V^T B, column tiles 7 yp .. 7 yp + 6 (13 tiles cover nz <= 104)
+    constexpr int ZQ = 7;
+    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
+    double acc[ZQ][2];
+#pragma unroll
+    for (int q = 0; q < ZQ; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+    double bcur[2][ZQ], bnxt[2][ZQ];
+    auto fetch = [&](int s0, double (&dst)[2][ZQ]) {      // B fragments of k-steps s0, s0 + 1 (rows 4 s + fk)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int row = i0 + 4 * (s0 + u) + fk;
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) {
+          const int c = 8 * (ZQ * yp + q) + fr;
+          dst[u][q] = (row < n && c < a.nz) ? Bq[(size_t)row * a.ldb + c] : 0.0;
+        }
+      }
+    };
+    fetch(0, bcur);
+#pragma unroll 1
+    for (int s0 = 0; s0 < SY_BM / 4; s0 += 2) {
+      if (s0 + 2 < SY_BM / 4) fetch(s0 + 2, bnxt);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const double av = Vs[(4 * (s0 + u) + fk) * DM_S + 8 * x + fr];
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) dmma884(acc[q][0], acc[q][1], av, bcur[u][q]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) bcur[u][q] = bnxt[u][q];
+    }
+    double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW + (size_t)(8 * x + fr) * SY_ZW;
+#pragma unroll
+    for (int q = 0; q < ZQ; ++q) {
+      const int c = 8 * (ZQ * yp + q) + 2 * fk;
+      if (c < a.nz) Zp[c] = acc[q][0];
+      if (c + 1 < a.nz) Zp[c + 1] = acc[q][1];
+    }
+    return;
+  }
+  double* Y0 = a.Y + (size_t)t * n * NB;
+  for (int e = tid; e < SY_BM * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    const bool ok = i0 + rl < n;
+    double yv = 0.0;
+    if (ok) {
+      for (int sp = 0; sp < a.nsplit; ++sp) yv += a.Y[((size_t)sp * a.T + t) * n * NB + (size_t)(i0 + rl) * NB + c];
+      if (a.nsplit > 1) Y0[(size_t)(i0 + rl) * NB + c] = yv;
+    }
+    Ys[rl * DM_S + c] = yv;
+    Vs[rl * DM_S + c] = ok ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
+  }
+  __syncthreads();
+  // out[r][c] = sum_rows L[row][r] R[row][c] for r = 8 x + fr, c = 16 yp + 8 j + 2 fk + {0, 1}
+  auto tn_product = [&](const double* L, const double* R, double* out) {
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 8
+    for (int s_ = 0; s_ < SY_BM / 4; ++s_) {
+      const double av = L[(4 * s_ + fk) * DM_S + 8 * x + fr];
+      dmma884(acc[0][0], acc[0][1], av, R[(4 * s_ + fk) * DM_S + 16 * yp + fr]);
+      dmma884(acc[1][0], acc[1][1], av, R[(4 * s_ + fk) * DM_S + 16 * yp + 8 + fr]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<double2*>(out + (8 * x + fr) * NB + 16 * yp + 8 * j + 2 * fk) = make_double2(acc[j][0], acc[j][1]);
+  };
+  tn_product(Vs, Ys, a.Mpart + ((size_t)t * a.nblk + bx) * NB * NB);            // V^T Y
+  if (a.Gpart) {
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const double* src = (which == 0 ? a.Wa : a.Va) + (size_t)t * n * LDV;
+      __syncthreads();                       // Ys (Y rows, then W_a rows) has been consumed
+      for (int e = tid; e < SY_BM * NB; e += 256) {
+        const int rl = e / NB, c = e % NB;
+        Ys[rl * DM_S + c] = (i0 + rl < n) ? src[(size_t)(i0 + rl) * LDV + c] : 0.0;
+      }
+      __syncthreads();
+      tn_product(Ys, Vs, a.Gpart + (((size_t)t * a.nblk + bx) * 2 + which) * NB * NB);   // W_a^T V, V_a^T V
+    }
+  }
+}
+
 // ------------------------------------------------------------------ thin update of the next panel's block column
 // Second panel of a deferred-update group (columns c0 .. c0+NB-1, rows >= c0): bring the block column up to date with
 // the first panel's reflector before its QR,  A[i][j] -= V_a[i] . W_a[j] + W_a[i] . V_a[j]   (lower part, i >= j).
@@ -1391,6 +1656,8 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
   const int nblk = (m + SY_BM - 1) / SY_BM;
   const bool has_z = B && nz > 0, has_g = q > 0;
   const double* Vq = bb.V + q * NB;
+  // DMMA forms of the small products: double2 accesses to the Z block need even ldb / nz and at most 13 column tiles
+  const bool dmma_small = pl->small_dmma && (!has_z || ((ldb & 1) == 0 && (nz & 1) == 0 && nz <= 104));
   int rc;
   // split-K so that the launch fills the machine (2 CTAs per SM) at least ~twice, while every CTA keeps a few chunks
   int S = 1;
@@ -1415,7 +1682,8 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     if (!pl->symm_tma) CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
     if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
-    symm_partials_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, SP_SMEM, st>>>(a);
+    if (dmma_small) partials_dmma_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, PD_SMEM, st>>>(a);
+    else symm_partials_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, SP_SMEM, st>>>(a);
     CHD_LAUNCHED();
   }
   {
@@ -1438,14 +1706,20 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     a.V = Vq; a.Y = bb.Y; a.W = bb.W + q * NB; a.nsplit = 1; a.T = T;   // split partials already summed
     a.Tf = bb.Tf + (size_t)slot * NB * NB; a.tf_stride = bb.tf_stride; a.TM = bb.TM;
     a.Gred = has_g ? bb.Gred : nullptr; a.Va = bb.V; a.Wa = bb.W; a.n = n; a.r0 = r0;
-    wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
-    CHD_LAUNCHED();
-  }
-  if (has_z) {
-    ZupdArgs a;
-    a.V = Vq; a.TZ = bb.TZ; a.Bq = B; a.ldb = ldb; a.nz = nz; a.n = n; a.r0 = r0;
-    zupdate_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, ZU_SMEM, st>>>(a);
-    CHD_LAUNCHED();
+    ZupdArgs z;
+    z.V = Vq; z.TZ = bb.TZ; z.Bq = B; z.ldb = ldb; z.nz = nz; z.n = n; z.r0 = r0;
+    if (dmma_small) {
+      // W and the Z-block update of a row block in one pass (both only need V's rows and the small matrices)
+      wz_dmma_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WZ_SMEM, st>>>(a, z, has_z ? 1 : 0);
+      CHD_LAUNCHED();
+    } else {
+      wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
+      CHD_LAUNCHED();
+      if (has_z) {
+        zupdate_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, ZU_SMEM, st>>>(z);
+        CHD_LAUNCHED();
+      }
+    }
   }
   if ((rc = profile_mark_end(PROF_WFORM, st))) return rc;
   return CHD_OK;
@@ -1486,13 +1760,19 @@ int band_device_init(Plan* pl) {
   CHD_CUDA(cudaFuncSetAttribute(symm_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(zupdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZU_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(wz_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WZ_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(partials_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
+  pl->small_dmma = getenv("CHD_SMALL_DMMA") ? atoi(getenv("CHD_SMALL_DMMA")) : 1;
   CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)syr2k_smem<64, 1>()));
   CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<32, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)syr2k_smem<32, 2>()));
   CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
   CHD_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CHD_CUDA(cudaFuncSetAttribute(panel_qr_reg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)RG_SMEM2));
   CHD_CUDA(cudaFuncSetAttribute(backtransform2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)pl->smem_optin));
   // panels per deferred-update group (CHD_KD=1: trailing update after every panel)
@@ -1505,6 +1785,7 @@ int band_device_init(Plan* pl) {
   const char* e = getenv("CHD_QR_REG");     // tuning / test switch: 0 disables the register-resident kernel
   if (e && atoi(e) == 0) {
     pl->qr_reg_max_cs = 0;
+    pl->qr_two = 0;
   } else {
     pl->qr_reg_max_cs = 8;
     cudaLaunchConfig_t cfg = {};
@@ -1514,10 +1795,16 @@ int band_device_init(Plan* pl) {
     cfg.attrs = at; cfg.numAttrs = 1;
     cfg.gridDim = dim3(16, 1); cfg.blockDim = dim3(RG_THREADS); cfg.dynamicSmemBytes = 0;
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, panel_qr_reg_kernel, &cfg) == cudaSuccess && nclusters > 0)
+    cfg.dynamicSmemBytes = RG_SMEM2;          // the two-row variant is the more demanding one
+    if (cudaOccupancyMaxActiveClusters(&nclusters, panel_qr_reg_kernel<true>, &cfg) == cudaSuccess && nclusters > 0)
       pl->qr_reg_max_cs = 16;
     else
       (void)cudaGetLastError();
+    pl->qr_two = getenv("CHD_QR_TWO") ? atoi(getenv("CHD_QR_TWO")) : 1;
+    if (const char* c = getenv("CHD_QR_REG_MAXCS")) {   // test switch: smaller clusters reach the two-row variant early
+      const int v = atoi(c);
+      if ((v == 1 || v == 2 || v == 4 || v == 8) && v < pl->qr_reg_max_cs) pl->qr_reg_max_cs = v;
+    }
   }
   return CHD_OK;
 }
@@ -1567,13 +1854,22 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
       cfg.stream = st;
       int rcs = 1;
       while (rcs < reg_max_cs && (m + rcs - 1) / rcs > RG_THREADS) rcs *= 2;
-      if (reg_max_cs > 0 && (m + rcs - 1) / rcs <= RG_THREADS) {
+      // One CTA per SM and a latency-bound column loop: when the one-row clusters of the T matrices need more than
+      // one wave, half as many CTAs with two rows per thread (second row in shared memory, ~1.3x per column) win
+      // (n = 8192, 64 matrices: 4.19 -> 3.06 ms per matrix).  CHD_QR_TWO: 0 only when needed, 1 auto, 2 always.
+      if (rcs > 1 && (m + rcs - 1) / rcs <= RG_THREADS &&
+          (pl->qr_two == 2 || (pl->qr_two == 1 && (long)T * rcs > pl->sm_count)))
+        rcs /= 2;
+      if (reg_max_cs > 0 && (m + rcs - 1) / rcs <= 2 * RG_THREADS) {
+        // one row per thread in registers; a second one in shared memory when the cluster is too small for that
+        const bool two = (m + rcs - 1) / rcs > RG_THREADS;
         a.RP = (m + rcs - 1) / rcs; a.RS = 0;
         cfg.gridDim = dim3(rcs, T);
         cfg.blockDim = dim3(RG_THREADS);
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = two ? RG_SMEM2 : 0;
         at[0].val.clusterDim.x = rcs;
-        CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_reg_kernel, a));
+        if (two) CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_reg_kernel<true>, a));
+        else CHD_CUDA(cudaLaunchKernelEx(&cfg, panel_qr_reg_kernel<false>, a));
       } else {
         const int cs = qr_cluster_size(pl, m, a.RP, a.RS, smem);
         cfg.gridDim = dim3(cs, T);

@@ -46,6 +46,8 @@ struct Plan {
   int chase_wave;          // cap on matrices per bulge-chasing launch (0: none)
   size_t chase_l2_budget;  // bytes of work bands one bulge-chasing launch may touch
   int qr_reg_max_cs;       // largest cluster of the register-resident panel QR (0: disabled)
+  int qr_two;              // two-rows-per-thread panel QR: 0 only when the cluster is too small, 1 auto, 2 always
+  int small_dmma;          // 1: per-panel small products (V^T Y, V^T B, W, Z block) on the FP64 tensor cores
   int gram_downdate;       // 1: Gram cores as rank-r downdates of the shared G = X X^T when r < p
   int gauss_shared;        // 1: Gaussian activations of a batch share the per-pair factors (gauss_shared_kernel)
   int band_kd;             // panels per deferred trailing update of the dense -> band stage (1 or 2)

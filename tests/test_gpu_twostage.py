@@ -46,13 +46,25 @@ def _problem(n, seed=6):
     return Ks, gas
 
 
-@pytest.mark.parametrize("n", [3, 20, 33, 34, 70, 97, 200, 333, 1100, 2300])
-def test_band_reduce_backtransform_match_model(n, monkeypatch):
+@pytest.mark.parametrize("n,qr", [(3, ""), (20, ""), (33, ""), (34, ""), (70, ""), (97, ""), (200, ""), (333, ""),
+                                  (1100, ""), (2300, "fallback"), (1000, "two1"), (1100, "two1"), (2300, "two2"),
+                                  (2300, "two_auto"), (333, "fma"), (1100, "fma")])
+def test_band_reduce_backtransform_match_model(n, qr, monkeypatch):
     """Matrices 0-2 are the (numerically rank-deficient) mode Gram matrices: Q is not unique there, so only the
     quantities the regression consumes are compared; matrix 3 is well conditioned and is compared element-wise
-    with the NumPy model (same algorithm, same reflector conventions)."""
-    if n == 2300:
+    with the NumPy model (same algorithm, same reflector conventions).  `qr` selects the panel-QR kernel the large
+    panels go through: the register kernel (default), its two-rows-per-thread variant (the n > 8192 path, reached
+    here by capping the cluster size or by CHD_QR_TWO=2) or the shared-memory / in-place fallback; "fma" keeps the
+    FMA forms of the per-panel small products (default: DMMA, wz_dmma_kernel / partials_dmma_kernel)."""
+    if qr == "fallback":
+        monkeypatch.setenv("CHD_QR_REG", "0")
         monkeypatch.setenv("CHD_QR_MAXCS", "2")     # forces panel rows out of shared memory (in-place rows in L2)
+    elif qr == "two_auto":
+        monkeypatch.setenv("CHD_QR_TWO", "2")            # two rows per thread whenever the cluster can be halved
+    elif qr.startswith("two"):
+        monkeypatch.setenv("CHD_QR_REG_MAXCS", qr[3:])   # 512 < rows per CTA <= 1024: second row in shared memory
+    elif qr == "fma":
+        monkeypatch.setenv("CHD_SMALL_DMMA", "0")        # FMA forms of the per-panel small products
     nat = _native()
     Ks, gas = _problem(n)
     rng = np.random.default_rng(5)
