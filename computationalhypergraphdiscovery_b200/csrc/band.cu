@@ -1024,42 +1024,62 @@ __global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
 // read from global memory straight into fragment position.  CHD_SMALL_DMMA=0 keeps the FMA kernels.
 constexpr int DM_S = NB + 4;
 constexpr int DM_SZ = SY_ZW + 4;
-constexpr size_t WZ_SMEM = (size_t)(4 * NB * DM_S + NB * DM_SZ) * sizeof(double);
+constexpr size_t WZ_SMEM = (size_t)(4 * NB * DM_S) * sizeof(double);      // >= NB * DM_SZ doubles (the Z half)
+static_assert(4 * NB * DM_S >= NB * DM_SZ, "the Z operand must fit the W half's shared memory");
 constexpr size_t PD_SMEM = (size_t)(2 * SY_BM * DM_S) * sizeof(double);
 
-// W = (Y - V_a G1 - W_a G2 - 1/2 V T^T M) T  and  B -= V (T^T V^T B)  for one 64-row block: warp w owns rows 8 w .. 8 w + 7
-__global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu, int has_z) {
+// W = (Y - V_a G1 - W_a G2 - 1/2 V T^T M) T  (blockIdx.z = 0)  and  B -= V (T^T V^T B)  (blockIdx.z = 1) for one 64-row
+// block: warp w owns rows 8 w .. 8 w + 7.  The two halves are independent, so they run as separate CTAs (one round of
+// global loads per warp each) of one launch.
+__global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu) {
   extern __shared__ __align__(16) double smem[];
-  double* G1s = smem;                       // NB x DM_S each
-  double* G2s = G1s + NB * DM_S;
-  double* TMs = G2s + NB * DM_S;
-  double* Ts = TMs + NB * DM_S;
-  double* TZs = Ts + NB * DM_S;             // NB x DM_SZ
   const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int n = a.n, i = a.r0 + WF_BM * blockIdx.x + 8 * wid + fr;
   const bool ok = i < n;
-  const bool corr = a.Gred != nullptr;
   const double* V = a.V + (size_t)t * n * LDV;
-  {
-    const double* Tf = a.Tf + (size_t)t * a.tf_stride;
-    const double* TM = a.TM + (size_t)t * NB * NB;
-    const double* G = corr ? a.Gred + (size_t)t * 2 * NB * NB : nullptr;
-    for (int e = tid; e < NB * NB; e += 256) {
-      const int o = (e / NB) * DM_S + (e % NB);
-      TMs[o] = TM[e];
-      Ts[o] = Tf[e];
-      if (corr) { G1s[o] = G[e]; G2s[o] = G[NB * NB + e]; }
-    }
-    if (has_z) {
-      const double* TZ = zu.TZ + (size_t)t * NB * SY_ZW;
-      for (int e = tid; e < NB * SY_ZW; e += 256) TZs[(e / SY_ZW) * DM_SZ + (e % SY_ZW)] = TZ[e];
-    }
-  }
-  // this lane's A fragments of V (row i, k = 4 s + fk) and the accumulators (row i, columns 8 y + 2 fk + {0, 1}) = Y
+  // this lane's A fragments of V (row i, k = 4 s + fk)
   double av[NB / 4];
 #pragma unroll
   for (int s_ = 0; s_ < NB / 4; ++s_) av[s_] = ok ? V[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+  if (blockIdx.z == 1) {
+    // B[i][z] -= sum_k V[i][k] TZ[k][z]: 13 column tiles of 8 cover nz <= 104 (ldb and nz even: double2 accesses)
+    double* TZs = smem;                     // NB x DM_SZ
+    constexpr int ZT = 13;
+    double* Brow = zu.Bq + (size_t)t * n * zu.ldb + (size_t)i * zu.ldb;
+    double zc[ZT][2];
+#pragma unroll
+    for (int y = 0; y < ZT; ++y) {
+      const int c = 8 * y + 2 * fk;
+      double2 bv = make_double2(0.0, 0.0);
+      if (ok && c < zu.nz) bv = *reinterpret_cast<const double2*>(Brow + c);
+      zc[y][0] = bv.x; zc[y][1] = bv.y;
+    }
+    const double* TZ = zu.TZ + (size_t)t * NB * SY_ZW;
+    for (int e = tid; e < NB * SY_ZW / 2; e += 256) {
+      const int k = e / (SY_ZW / 2), c = 2 * (e % (SY_ZW / 2));
+      *reinterpret_cast<double2*>(TZs + k * DM_SZ + c) = *reinterpret_cast<const double2*>(TZ + k * SY_ZW + c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s_ = 0; s_ < NB / 4; ++s_)
+#pragma unroll
+      for (int y = 0; y < ZT; ++y) dmma884(zc[y][0], zc[y][1], -av[s_], TZs[(4 * s_ + fk) * DM_SZ + 8 * y + fr]);
+    if (ok) {
+#pragma unroll
+      for (int y = 0; y < ZT; ++y) {
+        const int c = 8 * y + 2 * fk;
+        if (c < zu.nz) *reinterpret_cast<double2*>(Brow + c) = make_double2(zc[y][0], zc[y][1]);
+      }
+    }
+    return;
+  }
+  double* G1s = smem;                       // NB x DM_S each
+  double* G2s = G1s + NB * DM_S;
+  double* TMs = G2s + NB * DM_S;
+  double* Ts = TMs + NB * DM_S;
+  const bool corr = a.Gred != nullptr;
+  // accumulators (row i, columns 8 y + 2 fk + {0, 1}) = Y
   double acc[NB / 8][2];
 #pragma unroll
   for (int y = 0; y < NB / 8; ++y) {
@@ -1079,6 +1099,17 @@ __global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu, 
     for (int s_ = 0; s_ < NB / 4; ++s_) {
       a1[s_] = ok ? -Va[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
       a2[s_] = ok ? -Wa[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+    }
+  }
+  {
+    const double* Tf = a.Tf + (size_t)t * a.tf_stride;
+    const double* TM = a.TM + (size_t)t * NB * NB;
+    const double* G = corr ? a.Gred + (size_t)t * 2 * NB * NB : nullptr;
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int o = (e / NB) * DM_S + (e % NB);
+      TMs[o] = TM[e];
+      Ts[o] = Tf[e];
+      if (corr) { G1s[o] = G[e]; G2s[o] = G[NB * NB + e]; }
     }
   }
   __syncthreads();
@@ -1114,35 +1145,68 @@ __global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu, 
 #pragma unroll
     for (int y = 0; y < NB / 8; ++y) *reinterpret_cast<double2*>(W + 8 * y + 2 * fk) = make_double2(wv[y][0], wv[y][1]);
   }
-  if (has_z) {
-    // B[i][z] -= sum_k V[i][k] TZ[k][z]: 13 column tiles of 8 cover nz <= 104 (ldb and nz even: double2 accesses)
-    constexpr int ZT = 13;
-    double* Brow = zu.Bq + (size_t)t * n * zu.ldb + (size_t)i * zu.ldb;
-    double zc[ZT][2];
+}
+
+// Zpart = V_I^T B_I of a 128-row block (32 x nz, K = 128 rows) in two halves of 64 rows: the rows of B and V are
+// staged in shared memory by 16-byte cp.async copies (whole rows, coalesced; B stride 108 == 12 mod 16 keeps the DMMA
+// fragment loads conflict-free), three CTAs per SM so that one CTA's copies overlap the others' DMMA chains.  Warp
+// (x, yh): rows 8 x .. 8 x + 7 of the product, column tiles 7 yh .. (13 tiles cover nz <= 104).
+constexpr int ZP_HB = 64;
+constexpr int ZP_SB = 108;
+constexpr size_t ZP_SMEM = (size_t)ZP_HB * (DM_S + ZP_SB) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 3) zpart_dmma_kernel(SymmArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* Vs = smem;                       // ZP_HB x DM_S
+  double* Bs = Vs + ZP_HB * DM_S;          // ZP_HB x ZP_SB
+  const int t = blockIdx.y, bx = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = a.n, i0 = a.r0 + SY_BM * bx;
+  const double* V = a.V + (size_t)t * n * LDV;
+  const double* Bq = a.Bq + (size_t)t * n * a.ldb;
+  const int x = wid & 3, yh = wid >> 2;
+  constexpr int ZQ = 7;
+  const int nq = yh ? 13 - ZQ : ZQ;        // column tiles of this warp
+  const int chunks = a.nz >> 1;            // 16-byte pieces of a row of B
+  double acc[ZQ][2];
 #pragma unroll
-    for (int y = 0; y < ZT; ++y) {
-      const int c = 8 * y + 2 * fk;
-      double2 bv = make_double2(0.0, 0.0);
-      if (ok && c < zu.nz) bv = *reinterpret_cast<const double2*>(Brow + c);
-      zc[y][0] = bv.x; zc[y][1] = bv.y;
+  for (int q = 0; q < ZQ; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+#pragma unroll 1
+  for (int h = 0; h < SY_BM / ZP_HB; ++h) {
+    const int rh = i0 + ZP_HB * h;
+    if (h) __syncthreads();                // the previous half has been consumed
+    for (int e = tid; e < ZP_HB * (NB / 2); e += 256) {
+      const int rl = e / (NB / 2), part = e % (NB / 2);
+      const bool ok = rh + rl < n;
+      cp_async16(Vs + rl * DM_S + 2 * part, ok ? V + (size_t)(rh + rl) * LDV + 2 * part : V, ok);
     }
-#pragma unroll
-    for (int s_ = 0; s_ < NB / 4; ++s_)
-#pragma unroll
-      for (int y = 0; y < ZT; ++y) dmma884(zc[y][0], zc[y][1], -av[s_], TZs[(4 * s_ + fk) * DM_SZ + 8 * y + fr]);
-    if (ok) {
-#pragma unroll
-      for (int y = 0; y < ZT; ++y) {
-        const int c = 8 * y + 2 * fk;
-        if (c < zu.nz) *reinterpret_cast<double2*>(Brow + c) = make_double2(zc[y][0], zc[y][1]);
-      }
+    for (int e = tid; e < ZP_HB * chunks; e += 256) {
+      const int rl = e / chunks, part = e - rl * chunks;
+      const bool ok = rh + rl < n;
+      cp_async16(Bs + rl * ZP_SB + 2 * part, ok ? Bq + (size_t)(rh + rl) * a.ldb + 2 * part : Bq, ok);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 4
+    for (int s_ = 0; s_ < ZP_HB / 4; ++s_) {
+      const double av = Vs[(4 * s_ + fk) * DM_S + 8 * x + fr];
+#pragma unroll
+      for (int q = 0; q < ZQ; ++q)
+        if (q < nq) dmma884(acc[q][0], acc[q][1], av, Bs[(4 * s_ + fk) * ZP_SB + 8 * (ZQ * yh + q) + fr]);
+    }
+  }
+  double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW + (size_t)(8 * x + fr) * SY_ZW;
+#pragma unroll
+  for (int q = 0; q < ZQ; ++q) {
+    const int c = 8 * (ZQ * yh + q) + 2 * fk;
+    if (q < nq && c < a.nz) Zp[c] = acc[q][0];
+    if (q < nq && c + 1 < a.nz) Zp[c + 1] = acc[q][1];
   }
 }
 
-// Partial products of a 128-row block (the DMMA form of symm_partials_kernel, same outputs):
-//   blockIdx.z = 0: sum of the split-K partials of Y, Mpart = V_I^T Y_I, Gpart = {W_a,I^T V_I, V_a,I^T V_I}
-//   blockIdx.z = 1: Zpart = V_I^T B_I
+// Partial products of a 128-row block (the DMMA form of symm_partials_kernel, same outputs): sum of the split-K
+// partials of Y, Mpart = V_I^T Y_I, Gpart = {W_a,I^T V_I, V_a,I^T V_I}
 __global__ void __launch_bounds__(256) partials_dmma_kernel(SymmArgs a) {
   extern __shared__ __align__(16) double smem[];
   double* Ys = smem;                       // SY_BM x DM_S
@@ -1152,55 +1216,6 @@ __global__ void __launch_bounds__(256) partials_dmma_kernel(SymmArgs a) {
   const int n = a.n, i0 = a.r0 + SY_BM * bx;
   const double* V = a.V + (size_t)t * n * LDV;
   const int x = wid & 3, yp = wid >> 2;    // output rows 8 x .. (a column block of V^T), half of the output columns
-  if (blockIdx.z == 1) {
-    if (!(a.Bq && a.nz > 0)) return;
-    for (int e = tid; e < SY_BM * NB; e += 256) {
-      const int rl = e / NB, c = e % NB;
-      Vs[rl * DM_S + c] = (i0 + rl < n) ? V[(size_t)(i0 + rl) * LDV + c] : 0.0;
-    }
-    __syncthreads();
-    // warp (x, yp): rows 8 x .. 8 x + 7 of V^T B, column tiles 7 yp .. 7 yp + 6 (13 tiles cover nz <= 104)
-    constexpr int ZQ = 7;
-    const double* Bq = a.Bq + (size_t)t * n * a.ldb;
-    double acc[ZQ][2];
-#pragma unroll
-    for (int q = 0; q < ZQ; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
-    double bcur[2][ZQ], bnxt[2][ZQ];
-    auto fetch = [&](int s0, double (&dst)[2][ZQ]) {      // B fragments of k-steps s0, s0 + 1 (rows 4 s + fk)
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int row = i0 + 4 * (s0 + u) + fk;
-#pragma unroll
-        for (int q = 0; q < ZQ; ++q) {
-          const int c = 8 * (ZQ * yp + q) + fr;
-          dst[u][q] = (row < n && c < a.nz) ? Bq[(size_t)row * a.ldb + c] : 0.0;
-        }
-      }
-    };
-    fetch(0, bcur);
-#pragma unroll 1
-    for (int s0 = 0; s0 < SY_BM / 4; s0 += 2) {
-      if (s0 + 2 < SY_BM / 4) fetch(s0 + 2, bnxt);
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const double av = Vs[(4 * (s0 + u) + fk) * DM_S + 8 * x + fr];
-#pragma unroll
-        for (int q = 0; q < ZQ; ++q) dmma884(acc[q][0], acc[q][1], av, bcur[u][q]);
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int q = 0; q < ZQ; ++q) bcur[u][q] = bnxt[u][q];
-    }
-    double* Zp = a.Zpart + ((size_t)t * a.nblk + bx) * NB * SY_ZW + (size_t)(8 * x + fr) * SY_ZW;
-#pragma unroll
-    for (int q = 0; q < ZQ; ++q) {
-      const int c = 8 * (ZQ * yp + q) + 2 * fk;
-      if (c < a.nz) Zp[c] = acc[q][0];
-      if (c + 1 < a.nz) Zp[c + 1] = acc[q][1];
-    }
-    return;
-  }
   double* Y0 = a.Y + (size_t)t * n * NB;
   for (int e = tid; e < SY_BM * NB; e += 256) {
     const int rl = e / NB, c = e % NB;
@@ -1294,6 +1309,58 @@ __global__ void __launch_bounds__(256) panel_update_kernel(PupdArgs a) {
   for (int q = 0; q < PU_BM / 8; ++q) {
     const int i = i0 + wid + 8 * q;
     if (i < n && j < n && j <= i) A[(size_t)i * a.ldk + j] -= acc[q];
+  }
+}
+
+// DMMA form of the thin update: warp w of a 64-row block owns rows 8 w .. 8 w + 7 (A fragments of V_a / W_a straight
+// from global memory, accumulators = the 8 x 32 piece of the block column), the 32 rows c0 .. of W_a / V_a are the B
+// operands in shared memory.
+constexpr size_t PUD_SMEM = (size_t)(2 * NB * DM_S) * sizeof(double);
+
+__global__ void __launch_bounds__(256) pupd_dmma_kernel(PupdArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* VJ = smem;                        // NB x DM_S  (rows c0 .. c0+NB-1 of V_a / W_a)
+  double* WJ = VJ + NB * DM_S;
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = a.n, c0 = a.c0, i = c0 + PU_BM * blockIdx.x + 8 * wid + fr;
+  const bool ok = i < n;
+  const double* Va = a.Va + (size_t)t * n * LDV;
+  const double* Wa = a.Wa + (size_t)t * n * LDV;
+  double* Arow = a.A + (size_t)t * a.strideA + (size_t)i * a.ldk + c0;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int rl = e / NB, c = e % NB;
+    const bool okj = c0 + rl < n;
+    VJ[rl * DM_S + c] = okj ? Va[(size_t)(c0 + rl) * LDV + c] : 0.0;
+    WJ[rl * DM_S + c] = okj ? Wa[(size_t)(c0 + rl) * LDV + c] : 0.0;
+  }
+  double va[NB / 4], wa[NB / 4], acc[NB / 8][2];
+#pragma unroll
+  for (int s_ = 0; s_ < NB / 4; ++s_) {
+    va[s_] = ok ? -Va[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+    wa[s_] = ok ? -Wa[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+  }
+#pragma unroll
+  for (int y = 0; y < NB / 8; ++y) {
+    double2 av = make_double2(0.0, 0.0);
+    if (ok) av = *reinterpret_cast<const double2*>(Arow + 8 * y + 2 * fk);
+    acc[y][0] = av.x; acc[y][1] = av.y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s_ = 0; s_ < NB / 4; ++s_)
+#pragma unroll
+    for (int y = 0; y < NB / 8; ++y) {
+      dmma884(acc[y][0], acc[y][1], va[s_], WJ[(8 * y + fr) * DM_S + 4 * s_ + fk]);   // -= V_a[i] . W_a[j]
+      dmma884(acc[y][0], acc[y][1], wa[s_], VJ[(8 * y + fr) * DM_S + 4 * s_ + fk]);   // -= W_a[i] . V_a[j]
+    }
+  if (ok) {
+#pragma unroll
+    for (int y = 0; y < NB / 8; ++y) {
+      const int j = c0 + 8 * y + 2 * fk;                     // lower part only: j <= i
+      if (j + 1 <= i) *reinterpret_cast<double2*>(Arow + 8 * y + 2 * fk) = make_double2(acc[y][0], acc[y][1]);
+      else if (j <= i) Arow[8 * y + 2 * fk] = acc[y][0];
+    }
   }
 }
 
@@ -1682,8 +1749,15 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     if (!pl->symm_tma) CHD_LAUNCHED();
     if ((rc = profile_mark_end(PROF_SYMM, st))) return rc;
     if ((rc = profile_mark_begin(PROF_WFORM, st))) return rc;
-    if (dmma_small) partials_dmma_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, PD_SMEM, st>>>(a);
-    else symm_partials_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, SP_SMEM, st>>>(a);
+    if (dmma_small) {
+      if (has_z) {
+        zpart_dmma_kernel<<<dim3(nblk, T), 256, ZP_SMEM, st>>>(a);
+        CHD_LAUNCHED();
+      }
+      partials_dmma_kernel<<<dim3(nblk, T), 256, PD_SMEM, st>>>(a);
+    } else {
+      symm_partials_kernel<<<dim3(nblk, T, has_z ? 2 : 1), 256, SP_SMEM, st>>>(a);
+    }
     CHD_LAUNCHED();
   }
   {
@@ -1709,8 +1783,8 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     ZupdArgs z;
     z.V = Vq; z.TZ = bb.TZ; z.Bq = B; z.ldb = ldb; z.nz = nz; z.n = n; z.r0 = r0;
     if (dmma_small) {
-      // W and the Z-block update of a row block in one pass (both only need V's rows and the small matrices)
-      wz_dmma_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WZ_SMEM, st>>>(a, z, has_z ? 1 : 0);
+      // W and the Z-block update of a row block in one launch (both only need V's rows and the small matrices)
+      wz_dmma_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T, has_z ? 2 : 1), 256, WZ_SMEM, st>>>(a, z);
       CHD_LAUNCHED();
     } else {
       wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
@@ -1762,6 +1836,7 @@ int band_device_init(Plan* pl) {
   CHD_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(wz_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WZ_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(partials_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(zpart_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZP_SMEM));
   pl->small_dmma = getenv("CHD_SMALL_DMMA") ? atoi(getenv("CHD_SMALL_DMMA")) : 1;
   CHD_CUDA(cudaFuncSetAttribute(syr2k_row_kernel<64, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)syr2k_smem<64, 1>()));
@@ -1839,7 +1914,8 @@ int band_reduce_launch(const Plan* pl, double* K, int ldk, const double* ga, int
         // bring this panel's block column up to date with the pending reflectors of its group
         PupdArgs u;
         u.A = K; u.strideA = strideA; u.ldk = ldk; u.Va = bb.V; u.Wa = bb.W; u.n = n; u.c0 = c0;
-        panel_update_kernel<<<dim3((n - c0 + PU_BM - 1) / PU_BM, T), 256, PU_SMEM, st>>>(u);
+        if (pl->small_dmma) pupd_dmma_kernel<<<dim3((n - c0 + PU_BM - 1) / PU_BM, T), 256, PUD_SMEM, st>>>(u);
+        else panel_update_kernel<<<dim3((n - c0 + PU_BM - 1) / PU_BM, T), 256, PU_SMEM, st>>>(u);
         CHD_LAUNCHED();
       }
       QrArgs a;
