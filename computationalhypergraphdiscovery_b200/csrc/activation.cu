@@ -265,10 +265,16 @@ __global__ void __launch_bounds__(256) gauss_pairs_kernel(const double* __restri
 // members active (multi-variable clusters containing the target itself or an impossible edge) are flagged and served
 // by gauss_pairs_kernel instead.
 constexpr int GS_IB = 8, GS_JB = 16;          // pair tile: 8 rows x 16 columns = 128 pairs = 32 k-steps
-constexpr int GS_TG = 32;                     // targets per group (4 DMMA row blocks)
-constexpr int GS_MP = GS_TG + 8;              // shared-memory pitch of M[pair][target] (== 8 mod 32: conflict free)
-constexpr int GS_CW = 64;                     // clusters per warp (8 DMMA column blocks), 512 per CTA pass
-constexpr size_t GS_SMEM = (size_t)2 * GS_IB * GS_JB * GS_MP * sizeof(double);
+// Two shapes of the contraction (TG targets per group = DMMA row blocks, CW clusters per warp = DMMA column blocks, TH
+// threads; the producer geometry needs TG = TH / 8):
+//   <32, 64, 256>  batches of up to 32 targets: 8 warps x 64 clusters = 512 clusters per pass
+//   <64, 16, 512>  larger batches: all 64 targets share one evaluation of every factor (half the exps of two 32-target
+//                  groups) and 16 warps hide the latency of the exp chains (ncu of the first shape at 64 targets: 2 warps
+//                  per scheduler, issue slots 26 % busy, DMMA 17 %, FP64 11 %: latency bound); 256 clusters per pass
+template <int TG> struct GsCfg {
+  static constexpr int MP = TG + 8;           // shared-memory pitch of M[pair][target] (== 8 mod 32: conflict free)
+  static constexpr size_t SMEM = (size_t)2 * GS_IB * GS_JB * MP * sizeof(double);
+};
 
 // clist = clusters that are alive with at least one active member for SOME target of the batch (compact, in
 // increasing order), nc = their number; flagged[t] = 1 if some alive cluster of target t is only partly active.
@@ -303,7 +309,8 @@ __global__ void __launch_bounds__(256) cluster_union_kernel(const uint8_t* __res
   }
 }
 
-__global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __restrict__ X, int n, int N, int C, int T,
+template <int TG, int CW, int TH>
+__global__ void __launch_bounds__(TH, 1) gauss_shared_kernel(const double* __restrict__ X, int n, int N, int C, int T,
                                                               const double* __restrict__ yb,
                                                               const int32_t* __restrict__ mem_off,
                                                               const int32_t* __restrict__ mem_idx,
@@ -313,10 +320,12 @@ __global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __re
                                                               const double* __restrict__ Pc, int ldk) {
   __shared__ double etab[64];
   extern __shared__ __align__(16) double gs_smem[];
+  static_assert(TG == TH / 8 && TG % 8 == 0 && CW % 8 == 0, "producer geometry");
+  constexpr int GS_MP = GsCfg<TG>::MP, MB = TG / 8, NBK = CW / 8, NW = TH / 32;
   constexpr int MS_SZ = GS_IB * GS_JB * GS_MP;                    // M[pair][target], double buffered
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
-  const int tg0 = blockIdx.y * GS_TG;                // first target of this group
+  const int tg0 = blockIdx.y * TG;                // first target of this group
   const int nc = *ncp;
   exp_table_load(etab);
   const int ib_n = (n + GS_IB - 1) / GS_IB, jb_n = (n + GS_JB - 1) / GS_JB;
@@ -348,21 +357,21 @@ __global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __re
       dst[(ip * GS_JB + b) * GS_MP + tp] = m;
     }
   };
-  for (int cpass = 0; cpass * (8 * GS_CW) < nc; ++cpass) {
-    const int cb = cpass * (8 * GS_CW) + wid * GS_CW;   // first compact cluster index of this warp
+  for (int cpass = 0; cpass * (NW * CW) < nc; ++cpass) {
+    const int cb = cpass * (NW * CW) + wid * CW;   // first compact cluster index of this warp
     // this lane's B-fragment clusters: compact index cb + 8 nb + fr
-    int cl_lo[8], cl_hi[8];
+    int cl_lo[NBK], cl_hi[NBK];
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
+    for (int nb = 0; nb < NBK; ++nb) {
       const int k = cb + 8 * nb + fr;
       if (k < nc) { const int c = clist[k]; cl_lo[nb] = mem_off[c]; cl_hi[nb] = mem_off[c + 1]; }
       else { cl_lo[nb] = 0; cl_hi[nb] = 0; }
     }
-    double acc[4][8][2];
+    double acc[MB][NBK][2];
 #pragma unroll
-    for (int mb = 0; mb < 4; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+      for (int nb = 0; nb < NBK; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
     // walk this CTA's tiles
     long long tile = blockIdx.x;
     int bi = 0;
@@ -395,9 +404,9 @@ __global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __re
           const int i = min(i0 + il, n - 1), j = min(j0 + jl, n - 1);
           const double* xi = X + (size_t)i * N;
           const double* xj = X + (size_t)j * N;
-          double bf[8];
+          double bf[NBK];
 #pragma unroll
-          for (int nb = 0; nb < 8; ++nb) {
+          for (int nb = 0; nb < NBK; ++nb) {
             double F = 1.0;
             for (int m = cl_lo[nb]; m < cl_hi[nb]; ++m) {
               const int d = mem_idx[m];
@@ -407,13 +416,13 @@ __global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __re
             bf[nb] = 1.0 - rcp_ge1(F);
           }
           const double* mp = M + (4 * q + fk) * GS_MP + fr;
-          double af[4];
+          double af[MB];
 #pragma unroll
-          for (int mb = 0; mb < 4; ++mb) af[mb] = mp[8 * mb];
+          for (int mb = 0; mb < MB; ++mb) af[mb] = mp[8 * mb];
 #pragma unroll
-          for (int mb = 0; mb < 4; ++mb)
+          for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+            for (int nb = 0; nb < NBK; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
         }
       }
       __syncthreads();
@@ -423,11 +432,11 @@ __global__ void __launch_bounds__(256, 1) gauss_shared_kernel(const double* __re
     }
     // partial sums of this CTA: rows = targets 8 mb + fr, columns = compact clusters cb + 8 nb + 2 fk + {0, 1}
 #pragma unroll
-    for (int mb = 0; mb < 4; ++mb) {
+    for (int mb = 0; mb < MB; ++mb) {
       const int t = tg0 + 8 * mb + fr;
       if (t >= T) continue;
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
+      for (int nb = 0; nb < NBK; ++nb)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int k = cb + 8 * nb + 2 * fk + h;
@@ -617,9 +626,14 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
                                                                         flagged);
       CHD_LAUNCHED();
       nblk_shared = pl->sm_count < GA_BLOCKS ? pl->sm_count : GA_BLOCKS;
-      gauss_shared_kernel<<<dim3(nblk_shared, (T + GS_TG - 1) / GS_TG), 256, GS_SMEM, st>>>(
-          X, n, N, C, T, yb, mem_off, mem_idx, clist, clist + C, 1.0 / (2.0 * kd->l * kd->l), gpart, nblk_shared, P,
-          ldk);
+      if (T > 32 && pl->gauss_shared != 2)
+        gauss_shared_kernel<64, 16, 512><<<dim3(nblk_shared, (T + 63) / 64), 512, GsCfg<64>::SMEM, st>>>(
+            X, n, N, C, T, yb, mem_off, mem_idx, clist, clist + C, 1.0 / (2.0 * kd->l * kd->l), gpart, nblk_shared, P,
+            ldk);
+      else
+        gauss_shared_kernel<32, 64, 256><<<dim3(nblk_shared, (T + 31) / 32), 256, GsCfg<32>::SMEM, st>>>(
+            X, n, N, C, T, yb, mem_off, mem_idx, clist, clist + C, 1.0 / (2.0 * kd->l * kd->l), gpart, nblk_shared, P,
+            ldk);
       CHD_LAUNCHED();
     }
     gauss_pairs_kernel<<<dim3(nblk, T), 256, smem, st>>>(XT, n, N, C, yb, w, mem_off, mem_idx,
@@ -636,7 +650,11 @@ int act_launch(const Plan* pl, const chd_kernel_desc* kd, const double* X, const
 
 int act_device_init(Plan* pl) {
   pl->gauss_shared = getenv("CHD_GAUSS_SHARED") ? atoi(getenv("CHD_GAUSS_SHARED")) : 1;
-  CHD_CUDA(cudaFuncSetAttribute(gauss_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_SMEM));
+  // CHD_GAUSS_SHARED: 1 (default) shared factors, shape by batch size; 2: always the 32-target shape; 0: per-target kernel
+  CHD_CUDA(cudaFuncSetAttribute(gauss_shared_kernel<32, 64, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)GsCfg<32>::SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(gauss_shared_kernel<64, 16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)GsCfg<64>::SMEM));
   // the kernel also has static shared memory: the opt-in limit covers static + dynamic
   cudaFuncAttributes fa;
   CHD_CUDA(cudaFuncGetAttributes(&fa, gauss_pairs_kernel));

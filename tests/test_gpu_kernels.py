@@ -205,12 +205,17 @@ def test_activations_match_oracle(clusters):
 
 
 
-@pytest.mark.parametrize("clusters,N,T", [(False, 40, 37), (True, 8, 8), (False, 8, 3)])
-def test_shared_gaussian_activations_match_oracle(clusters, N, T):
+@pytest.mark.parametrize("clusters,N,T,shape", [(False, 40, 37, ""), (False, 40, 37, "2"), (False, 40, 70, ""),
+                                                (False, 260, 33, ""), (True, 8, 8, ""), (False, 8, 3, "")])
+def test_shared_gaussian_activations_match_oracle(clusters, N, T, shape, monkeypatch):
     """gauss_shared_kernel (one evaluation of the per-pair factors for the whole batch + DMMA contraction; needs the
     cached product maps, so it is reached through chd_prune_chain) against the oracle's activations
     (helper_functions.py:113-132, kernels.py:270-278): more than one target group (T = 37 > 32), clustered variables
-    (targets inside a multi-variable cluster are flagged and served by gauss_pairs_kernel), few targets."""
+    (targets inside a multi-variable cluster are flagged and served by gauss_pairs_kernel), few targets.  Batches of more
+    than 32 targets take the 64-target shape of the kernel (T = 37: one partly filled group, T = 70: two groups,
+    N = 260: two passes over the clusters); shape "2" forces the 32-target shape (two groups at T = 37)."""
+    if shape:
+        monkeypatch.setenv("CHD_GAUSS_SHARED", shape)
     nat = _native()
     n = 150
     X, names = _data(n, N, 13)
@@ -245,7 +250,7 @@ def test_shared_gaussian_activations_match_oracle(clusters, N, T):
     torch.cuda.synchronize()
     act = out["act"][:, 0].cpu().numpy()
     pruned = out["pruned"][:, 0].cpu().numpy()
-    for t in range(T):
+    for t in (range(T) if N <= 64 else (0, T // 2, T - 1)):     # the oracle costs C full n x n x N products per target
         am = im * w0[t][None, :] * alive[t][:, None]
         ref = ochd.activations(spec, X, yb[t], ga[t], am, clusters)
         np.testing.assert_allclose(act[t], ref, rtol=1e-9, atol=1e-12)
