@@ -1018,20 +1018,61 @@ __global__ void __launch_bounds__(256) zupdate_kernel(ZupdArgs a) {
 // ------------------------------------------------------------------ the same small products on the FP64 tensor cores
 // The per-panel products of a row block with 32 x 32 / 32 x 100 matrices are GEMM-shaped (K = 32 or K = the block's
 // rows); as FMA loops they ran at 8 TFLOP/s with the FP64 pipe as the limiter (ncu: 27 % FP64 pipe, 15-25 % of the DRAM
-// bandwidth).  Here they are DMMA m8n8k4 chains: a warp owns 8 rows (wz_dmma_kernel) or a pair / a strip of 8 x 8
+// bandwidth).  Here they are DMMA m8n8k4 chains: a warp owns 8 rows (wform_dmma_kernel, zupd_dmma_kernel) or a pair / a strip of 8 x 8
 // output tiles (partials_dmma_kernel); 32 x 32 operands sit in shared memory with stride NB + 4 and the Z operand with
 // stride SY_ZW + 4 (== 4 mod 16: the four k-rows of a B fragment land in different bank groups), row operands are
 // read from global memory straight into fragment position.  CHD_SMALL_DMMA=0 keeps the FMA kernels.
 constexpr int DM_S = NB + 4;
 constexpr int DM_SZ = SY_ZW + 4;
-constexpr size_t WZ_SMEM = (size_t)(4 * NB * DM_S) * sizeof(double);      // >= NB * DM_SZ doubles (the Z half)
-static_assert(4 * NB * DM_S >= NB * DM_SZ, "the Z operand must fit the W half's shared memory");
+constexpr size_t WZ_SMEM = (size_t)(4 * NB * DM_S) * sizeof(double);
 constexpr size_t PD_SMEM = (size_t)(2 * SY_BM * DM_S) * sizeof(double);
 
-// W = (Y - V_a G1 - W_a G2 - 1/2 V T^T M) T  (blockIdx.z = 0)  and  B -= V (T^T V^T B)  (blockIdx.z = 1) for one 64-row
-// block: warp w owns rows 8 w .. 8 w + 7.  The two halves are independent, so they run as separate CTAs (one round of
-// global loads per warp each) of one launch.
-__global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu) {
+// B -= V (T^T V^T B) for one 64-row block: warp w owns rows 8 w .. 8 w + 7, blockIdx.z picks 7 of the 13 column tiles
+// (28 accumulator registers instead of 52: four CTAs per SM -- the kernel is one round of global loads, one DMMA
+// chain and one round of stores per warp, so it lives on occupancy).
+constexpr int ZU_T = 7;                           // column tiles per CTA
+constexpr int ZU_S = 8 * ZU_T + 4;                // stride of the staged 32 x 56 piece of T^T V^T B (== 12 mod 16)
+__global__ void __launch_bounds__(256, 4) zupd_dmma_kernel(ZupdArgs zu) {
+  __shared__ __align__(16) double TZs[NB * ZU_S];
+  const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = zu.n, i = zu.r0 + WF_BM * blockIdx.x + 8 * wid + fr;
+  const bool ok = i < n;
+  const int cb = 8 * ZU_T * blockIdx.z;           // first column of this CTA
+  const double* V = zu.V + (size_t)t * n * LDV;
+  double* Brow = zu.Bq + (size_t)t * n * zu.ldb + (size_t)i * zu.ldb + cb;
+  double zc[ZU_T][2];
+#pragma unroll
+  for (int y = 0; y < ZU_T; ++y) {
+    const int c = cb + 8 * y + 2 * fk;
+    double2 bv = make_double2(0.0, 0.0);
+    if (ok && c < zu.nz) bv = *reinterpret_cast<const double2*>(Brow + 8 * y + 2 * fk);
+    zc[y][0] = bv.x; zc[y][1] = bv.y;
+  }
+  double av[NB / 4];
+#pragma unroll
+  for (int s_ = 0; s_ < NB / 4; ++s_) av[s_] = ok ? -V[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
+  const double* TZ = zu.TZ + (size_t)t * NB * SY_ZW + cb;
+  for (int e = tid; e < NB * (4 * ZU_T); e += 256) {     // 32 rows x 28 double2
+    const int k = e / (4 * ZU_T), c = 2 * (e % (4 * ZU_T));
+    *reinterpret_cast<double2*>(TZs + k * ZU_S + c) = *reinterpret_cast<const double2*>(TZ + k * SY_ZW + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s_ = 0; s_ < NB / 4; ++s_)
+#pragma unroll
+    for (int y = 0; y < ZU_T; ++y) dmma884(zc[y][0], zc[y][1], av[s_], TZs[(4 * s_ + fk) * ZU_S + 8 * y + fr]);
+  if (ok) {
+#pragma unroll
+    for (int y = 0; y < ZU_T; ++y) {
+      const int c = cb + 8 * y + 2 * fk;
+      if (c < zu.nz) *reinterpret_cast<double2*>(Brow + 8 * y + 2 * fk) = make_double2(zc[y][0], zc[y][1]);
+    }
+  }
+}
+
+// W = (Y - V_a G1 - W_a G2 - 1/2 V T^T M) T for one 64-row block: warp w owns rows 8 w .. 8 w + 7
+__global__ void __launch_bounds__(256, 3) wform_dmma_kernel(WformArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
@@ -1042,38 +1083,6 @@ __global__ void __launch_bounds__(256) wz_dmma_kernel(WformArgs a, ZupdArgs zu) 
   double av[NB / 4];
 #pragma unroll
   for (int s_ = 0; s_ < NB / 4; ++s_) av[s_] = ok ? V[(size_t)i * LDV + 4 * s_ + fk] : 0.0;
-  if (blockIdx.z == 1) {
-    // B[i][z] -= sum_k V[i][k] TZ[k][z]: 13 column tiles of 8 cover nz <= 104 (ldb and nz even: double2 accesses)
-    double* TZs = smem;                     // NB x DM_SZ
-    constexpr int ZT = 13;
-    double* Brow = zu.Bq + (size_t)t * n * zu.ldb + (size_t)i * zu.ldb;
-    double zc[ZT][2];
-#pragma unroll
-    for (int y = 0; y < ZT; ++y) {
-      const int c = 8 * y + 2 * fk;
-      double2 bv = make_double2(0.0, 0.0);
-      if (ok && c < zu.nz) bv = *reinterpret_cast<const double2*>(Brow + c);
-      zc[y][0] = bv.x; zc[y][1] = bv.y;
-    }
-    const double* TZ = zu.TZ + (size_t)t * NB * SY_ZW;
-    for (int e = tid; e < NB * SY_ZW / 2; e += 256) {
-      const int k = e / (SY_ZW / 2), c = 2 * (e % (SY_ZW / 2));
-      *reinterpret_cast<double2*>(TZs + k * DM_SZ + c) = *reinterpret_cast<const double2*>(TZ + k * SY_ZW + c);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int s_ = 0; s_ < NB / 4; ++s_)
-#pragma unroll
-      for (int y = 0; y < ZT; ++y) dmma884(zc[y][0], zc[y][1], -av[s_], TZs[(4 * s_ + fk) * DM_SZ + 8 * y + fr]);
-    if (ok) {
-#pragma unroll
-      for (int y = 0; y < ZT; ++y) {
-        const int c = 8 * y + 2 * fk;
-        if (c < zu.nz) *reinterpret_cast<double2*>(Brow + c) = make_double2(zc[y][0], zc[y][1]);
-      }
-    }
-    return;
-  }
   double* G1s = smem;                       // NB x DM_S each
   double* G2s = G1s + NB * DM_S;
   double* TMs = G2s + NB * DM_S;
@@ -1783,9 +1792,12 @@ static int slot_launch(const Plan* pl, double* K, int ldk, int T, double* B, int
     ZupdArgs z;
     z.V = Vq; z.TZ = bb.TZ; z.Bq = B; z.ldb = ldb; z.nz = nz; z.n = n; z.r0 = r0;
     if (dmma_small) {
-      // W and the Z-block update of a row block in one launch (both only need V's rows and the small matrices)
-      wz_dmma_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T, has_z ? 2 : 1), 256, WZ_SMEM, st>>>(a, z);
+      wform_dmma_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WZ_SMEM, st>>>(a);
       CHD_LAUNCHED();
+      if (has_z) {
+        zupd_dmma_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T, (nz + 8 * ZU_T - 1) / (8 * ZU_T)), 256, 0, st>>>(z);
+        CHD_LAUNCHED();
+      }
     } else {
       wform_kernel<<<dim3((m + WF_BM - 1) / WF_BM, T), 256, WF_SMEM, st>>>(a);
       CHD_LAUNCHED();
@@ -1834,7 +1846,7 @@ int band_device_init(Plan* pl) {
   CHD_CUDA(cudaFuncSetAttribute(symm_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(zupdate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZU_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PU_SMEM));
-  CHD_CUDA(cudaFuncSetAttribute(wz_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WZ_SMEM));
+  CHD_CUDA(cudaFuncSetAttribute(wform_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WZ_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(partials_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
   CHD_CUDA(cudaFuncSetAttribute(zpart_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZP_SMEM));
   pl->small_dmma = getenv("CHD_SMALL_DMMA") ? atoi(getenv("CHD_SMALL_DMMA")) : 1;
