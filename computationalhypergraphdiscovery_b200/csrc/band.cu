@@ -1583,14 +1583,22 @@ __global__ void __cluster_dims__(BT_CS, 1, 1) __launch_bounds__(BT_THREADS) back
     for (int e = tid; e < NB * NB; e += BT_THREADS) Ts[(e / NB) * (NB + 1) + (e % NB)] = Tf[e];
     const int lo = max(row_lo, r0);
     // ---- c = V^T x over the owned rows: lanes = reflector columns, 4 rows in flight per warp iteration
+    // (four rows' loads in flight per warp; ONE accumulator, rows in increasing order: the sum is bit-identical to the
+    // rolled loop, which spent its time in one exposed HBM latency per row)
+    auto vmask = [&](double v, int pr) {
+      if (pr < NB) return (lane >= nref || pr < lane) ? 0.0 : ((pr == lane) ? 1.0 : v);
+      return (lane >= nref) ? 0.0 : v;
+    };
     double acc = 0.0;
-    for (int i = lo + wid; i < row_hi; i += NW) {
-      const int pr = i - r0;
-      double v = A[(size_t)i * ldk + c0 + lane];
-      if (pr < NB) v = (lane >= nref || pr < lane) ? 0.0 : ((pr == lane) ? 1.0 : v);
-      else if (lane >= nref) v = 0.0;
-      acc = fma(v, xs[i - row_lo], acc);
+    int i = lo + wid;
+    for (; i + 3 * NW < row_hi; i += 4 * NW) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = A[(size_t)(i + u * NW) * ldk + c0 + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = fma(vmask(v[u], i + u * NW - r0), xs[i + u * NW - row_lo], acc);
     }
+    for (; i < row_hi; i += NW) acc = fma(vmask(A[(size_t)i * ldk + c0 + lane], i - r0), xs[i - row_lo], acc);
     red[wid * (NB + 1) + lane] = acc;
     __syncthreads();
     if (tid < NB) {
@@ -1616,13 +1624,19 @@ __global__ void __cluster_dims__(BT_CS, 1, 1) __launch_bounds__(BT_THREADS) back
     }
     __syncthreads();
     // ---- x -= V s
-    for (int i = lo + wid; i < row_hi; i += NW) {
-      const int pr = i - r0;
-      double v = A[(size_t)i * ldk + c0 + lane];
-      if (pr < NB) v = (lane >= nref || pr < lane) ? 0.0 : ((pr == lane) ? 1.0 : v);
-      else if (lane >= nref) v = 0.0;
-      double d = v * ss[lane];
-      d = warp_sum(d);
+    i = lo + wid;
+    for (; i + 3 * NW < row_hi; i += 4 * NW) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = A[(size_t)(i + u * NW) * ldk + c0 + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double d = warp_sum(vmask(v[u], i + u * NW - r0) * ss[lane]);
+        if (lane == 0) xs[i + u * NW - row_lo] -= d;
+      }
+    }
+    for (; i < row_hi; i += NW) {
+      const double d = warp_sum(vmask(A[(size_t)i * ldk + c0 + lane], i - r0) * ss[lane]);
       if (lane == 0) xs[i - row_lo] -= d;
     }
     __syncthreads();
